@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- one JSON line per run (contract in the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload riou|rnms|detect] [--impl ours|reference]
+
+Default (N=1): BASELINE.json configs[1] -- rotated IoU, 10k x 10k random (cx,cy,w,h,theta) boxes -> Mpairs/s.
+A "step" is one pass of the hot path over one batch of synthetic input.  `value` is measured with inputs
+resident in HBM; `e2e` goes through the public Python API with pinned HOST buffers (H2D + D2H inside the timed
+region).  `roofline` is for the dominant kernel (CUDA events on the launching stream, algorithmic bytes from
+SURVEY.md 8d); `cpu_baseline` is the reference's own kernel code compiled for the host (oracle/_ref, kind
+"reference") or the oracle port, on a bounded sample.  `--impl reference` times only that CPU path.
+Multi-GPU (torchrun): the path shards by independent row blocks / images, no data-path collective, weak scaling;
+time = max over ranks."""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py touches oracle/)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_threads():
+    return max(1, len(os.sched_getaffinity(0)))
+
+
+def cpu_riou(sample_rows, steps=1):
+    """reference IoU code on the host cores over `sample_rows` x 10k pairs of the config-2 workload"""
+    import numpy as np
+    import helpers
+    a = np.concatenate([helpers.gen_boxes(10000, 0).numpy(), np.zeros((10000, 1), np.float32)], 1)[:sample_rows]
+    b = np.concatenate([helpers.gen_boxes(10000, 1).numpy(), np.zeros((10000, 1), np.float32)], 1)
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    out = np.empty((sample_rows, 10000), np.float32)
+    ref = helpers.ref_lib("host")
+    th = cpu_threads()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        if ref is not None:
+            ref.ref_host_iou_pairwise(helpers.P(a), sample_rows, helpers.P(b), 10000, 6, helpers.P(out), th)
+            kind, cores = "reference", th
+        else:
+            helpers.oracle().orc_skew_iou_pairwise(helpers.P(a), sample_rows, 6, helpers.P(b), 10000, 6, 0, helpers.P(out))
+            kind, cores = "port", 1
+        times.append(time.perf_counter() - t0)
+    pairs = sample_rows * 10000
+    what = ("reference device IoU code (rotate_polygon_nms_kernel.cu:22-260) as host C++, OpenMP" if kind == "reference"
+            else "oracle float64 clip (orc_skew_iou), scalar")
+    return {"value": pairs / min(times) / 1e6, "unit": "Mpairs/s", "cores": cores, "kind": kind,
+            "sample": "%d x 10000 pairs of the 10k x 10k workload; %s" % (sample_rows, what)}, times
+
+
+def cpu_rnms(n, steps=1):
+    import numpy as np
+    import helpers
+    dets = helpers.gen_dets(n, 2).numpy()
+    keep = np.empty(n, np.int64)
+    ref = helpers.ref_lib("host")
+    th = cpu_threads()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        if ref is not None:
+            k = ref.ref_host_rnms(helpers.P(dets), n, ctypes.c_float(0.5), keep.ctypes.data_as(helpers.I64P), th, None, None)
+            kind, cores = "reference", th
+        else:
+            k = len(helpers.orc_rnms(dets, 0.5))
+            kind, cores = "port", 1
+        times.append(time.perf_counter() - t0)
+    return {"value": n / min(times), "unit": "boxes/s", "cores": cores, "kind": kind,
+            "sample": "%d boxes (config-3 generator), thr 0.5, K=%d; upper-triangle IoU + reference serial scan" % (n, k)}, times
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="riou", choices=["riou", "rnms", "detect"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    metric = {"riou": ("rotated-IoU Mpairs/sec", "Mpairs/s"), "rnms": ("RNMS boxes/sec", "boxes/s"),
+              "detect": ("608x608 images/sec", "images/s")}[args.workload]
+
+    if args.impl == "reference":
+        # reference arm: the reference's own CPU implementation of the path on the host cores, rank 0 only
+        if rank != 0:
+            return
+        if args.workload == "riou":
+            cb, times = cpu_riou(sample_rows=16 * cpu_threads(), steps=max(1, min(K, 3)) + min(W, 1))
+            workload = "rotated IoU 10k x 10k (config 2), bounded sample per step"
+        elif args.workload == "rnms":
+            cb, times = cpu_rnms(4000, steps=max(1, min(K, 3)))
+            workload = "rotated NMS (config 3), bounded sample of 4000 boxes per step"
+        else:
+            print(json.dumps({"impl": "reference", "unavailable": "detect workload has no CPU reference arm yet"}))
+            return
+        print(json.dumps({"impl": "reference", "metric": metric[0], "value": cb["value"], "unit": metric[1],
+                          "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * min(times),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
+                          "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": metric[1], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import helpers
+    import rotate_yolov3_b200 as pkg
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    lib = pkg._lib.lib
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- workload setup ----------------
+    if args.workload == "riou":
+        n = m = 10000
+        a_h = helpers.gen_boxes(n, 100 * rank).pin_memory()   # rank r owns row block r of a (world*10k) x 10k problem
+        b_h = helpers.gen_boxes(m, 1).pin_memory()
+        a, b = a_h.to(dev), b_h.to(dev)
+        outs = [torch.empty((n, m), dtype=torch.float32, device=dev) for _ in range(2)]
+        out_h = torch.empty((n, m), dtype=torch.float32).pin_memory()
+        units = n * m
+        alg_bytes = 20 * (n + m) + 4 * n * m      # 400 400 000 B per call
+        launches_per_step = 1
+
+        def step(i):
+            pkg.rotated_iou_matrix(a, b, out=outs[i & 1])
+
+        def step_e2e(i):
+            ad = a_h.to(dev, non_blocking=True)
+            bd = b_h.to(dev, non_blocking=True)
+            pkg.rotated_iou_matrix(ad, bd, out=outs[i & 1])
+            out_h.copy_(outs[i & 1], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d, d2h = (n + m) * 5 * 4, n * m * 4
+        cfg = {"workload": "rotated IoU, N=M=10000 random (cx,cy,w,h,theta) boxes on a 608^2 canvas (BASELINE configs[1])",
+               "mode": "iou", "sharding": "row blocks of A per rank, B replicated, no collective",
+               "l2": "each step streams a 400 MB output (> 126 MB L2) into alternating buffers"}
+        scale = 1e-6
+    elif args.workload == "rnms":
+        n = 20000
+        d_h = helpers.gen_dets(n, 2 + 100 * rank).pin_memory()
+        d = d_h.to(dev)
+        units = n
+        cbk = (n + 63) // 64
+        alg_bytes = 24 * n + 8 * n * cbk * 2       # boxes in + mask write + mask read (reference algorithm)
+        launches_per_step = 8
+        flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
+        keep_h = torch.empty(n, dtype=torch.long).pin_memory()
+
+        def step(i):
+            pkg.r_nms(d, 0.5)
+
+        def step_e2e(i):
+            dd = d_h.to(dev, non_blocking=True)
+            k = pkg.r_nms(dd, 0.5)
+            keep_h[:len(k)].copy_(k)
+        h2d, d2h = n * 6 * 4, 8 * 8666
+        cfg = {"workload": "rotated NMS, 20000 boxes/image, 1 class, IoU thr 0.5 (BASELINE configs[2])",
+               "sharding": "one image per rank (replicas), no collective",
+               "l2": "50 MB mask rewritten every step; 192 MB flush buffer written between timed steps"}
+        scale = 1.0
+    else:
+        raise SystemExit("detect workload: conv path not built yet")
+
+    # ---------------- device-resident timing ----------------
+    for i in range(W):
+        step(i)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = lib.ryolo_launch_count()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    flush_ms = 0.0
+    for i in range(K):
+        if args.workload == "rnms":
+            flush.fill_(i & 0xFF)   # L2 flush between timed iterations (not counted: per-step events below)
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    t_end.record()
+    barrier()
+    launches = lib.ryolo_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    per_step = [s.elapsed_time(e) for s, e in ev]
+    tot_ms = sum(per_step)
+    t = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms = float(t.item())
+    ms_per_step = tot_ms / K
+    value = units * world / (ms_per_step * 1e-3) * scale
+
+    # ---------------- end-to-end through the public API, host buffers ----------------
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    Ke = max(3, K // 2)
+    e0.record()
+    for i in range(Ke):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1) / Ke], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = units * world / (float(te.item()) * 1e-3) * scale
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    if args.workload == "riou":
+        kern_ms = sorted(per_step)[len(per_step) // 2]   # one launch per step: the step IS the kernel
+        kernel = "riou_pairwise_kernel"
+    else:
+        kern_ms = sorted(per_step)[len(per_step) // 2]
+        kernel = "rnms pipeline (rnms_mask_kernel dominant; see profiles/)"
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "traffic_%s.json" % args.workload)
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roof = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["src"] + " (burst copy)",
+            "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms}
+
+    out = {"metric": metric[0], "value": value, "unit": metric[1], "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": cfg, "roofline": roof,
+           "e2e": {"value": e2e_val, "unit": metric[1], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": float(te.item())},
+           "gpu_launches": int(launches), "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        if args.workload == "riou":
+            out["cpu_baseline"], _ = cpu_riou(sample_rows=16 * cpu_threads())
+        else:
+            out["cpu_baseline"], _ = cpu_rnms(4000)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

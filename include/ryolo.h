@@ -1,0 +1,129 @@
+/*
+ * ryolo.h -- C-ABI of the B200-native rotate-yolov3 hot path (libryolo.so).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / a CUDA stream handle
+ * (passed as void* so that this header needs no CUDA include), allocates nothing behind the
+ * caller's back (scratch comes from a caller-owned workspace whose size is queried first),
+ * never throws, and returns an int status: 0 = ok, <0 = RYOLO_E_* (see ryolo_last_error()).
+ * All data pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ * There is NO CPU fallback: without a CUDA device every compute call returns RYOLO_E_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo, ming71/rotate-yolov3):
+ *   ryolo_rnms*            <- r_nms(dets, thr)          utils/nms/src/rotate_polygon_nms.cpp:7-16
+ *                             nms_cuda()                utils/nms/src/rotate_polygon_nms_kernel.cu:323-384
+ *                             rotate_nms_kernel         utils/nms/src/rotate_polygon_nms_kernel.cu:262-308
+ *   ryolo_riou_*           <- skew_bbox_iou(box1, box2, GIoU)   utils/utils.py:290-320
+ *                             skewiou / get_rotated_coors        utils/utils.py:663-699, 702-725
+ *   ryolo_nms_filter       <- non_max_suppression() candidate filter  utils/nms/nms.py:34-40,55
+ *   ryolo_conv_*           <- Conv2d -> BatchNorm2d -> PReLU blocks built by create_modules
+ *                             model/models.py:49-66; folded BN per utils/torch_utils.py:45-69
+ *   ryolo_yolo_decode      <- YOLOLayer.forward eval branch   model/models.py:183-227,
+ *                             create_grids                     model/model_utils.py:16-35
+ */
+#ifndef RYOLO_H_
+#define RYOLO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RYOLO_OK 0
+#define RYOLO_E_ARG (-1)       /* bad argument (null pointer, negative size, unknown mode) */
+#define RYOLO_E_WORKSPACE (-2) /* workspace too small / misaligned                          */
+#define RYOLO_E_CUDA (-3)      /* CUDA runtime error (text in ryolo_last_error)             */
+#define RYOLO_E_UNSUPPORTED (-4)
+
+/* ABI version of this header; bumped on any signature change. */
+int ryolo_abi_version(void);
+/* Thread-local text of the last failure on the calling thread ("" if none). */
+const char* ryolo_last_error(void);
+/* Number of this library's kernel launches issued by the calling process so far
+ * (bench.py's `gpu_launches` evidence). */
+uint64_t ryolo_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Rotated NMS  (reference: r_nms / nms_cuda, rotate_polygon_nms_kernel.cu:323-384)
+ *
+ * dets     [n,6] fp32 (cx, cy, w, h, theta_rad, score), row-major, device.
+ * thr      suppress j iff IoU(i,j) > thr (strict), i = higher score; NaN IoU never suppresses.
+ * keep_out [n] int64, device: receives the ORIGINAL indices of the kept boxes, ASCENDING
+ *          (reference :380-383); only the first *num_keep entries are defined.
+ * num_keep device int32[1].
+ * The IoU arithmetic replicates the reference device code operation-for-operation, including
+ * the FMA contractions nvcc's default -fmad=true applies to it (DESIGN.md "pinned arithmetic"),
+ * so the kept index list is bit-identical to the reference kernel's on the same inputs when the
+ * scores are tie-free (the reference's torch sort is unstable; ours is a stable descending sort).
+ * Asynchronous on `stream`; no host synchronisation inside.
+ * ------------------------------------------------------------------------------------------ */
+size_t ryolo_rnms_workspace_bytes(int n);
+int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Introspection of the last ryolo_rnms call that used `workspace` (valid until the workspace is
+ * reused): device pointers to the score-sorted boxes [n,6], the sort permutation order[n]
+ * (int32, sorted position -> original index) and the suppression mask [n, ceil(n/64)] uint64 in the
+ * reference's layout (only words with column-block >= row-block are defined, as in the
+ * reference host scan :371-374).  Used by the parity tests to compare masks bit-for-bit. */
+int ryolo_rnms_debug_views(void* workspace, int n, const float** sorted_boxes,
+                           const int32_t** order, const unsigned long long** mask);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Rotated IoU  (reference: skew_bbox_iou, utils/utils.py:290-320)
+ *
+ * Boxes are rows of `stride` floats (stride >= 5) whose first five are (cx, cy, w, h, theta_rad);
+ * corners per get_rotated_coors (utils/utils.py:702-725).  mode: 0 = 'iou'
+ * (inter / (A1 + A2 - inter)), 1 = 'giou' as the reference defines it (inter / area of the
+ * axis-aligned envelope of the 8 corners, utils/utils.py:682-685).  Zero-area boxes and a zero
+ * denominator give 0 (utils/utils.py:672-673, 693-694).  fp32 in/out; geometry is an fp32
+ * convex clip in box1's local frame (tolerance vs the float64 oracle: 1e-4 rel + 1e-6 abs).
+ * ------------------------------------------------------------------------------------------ */
+#define RYOLO_IOU_MODE_IOU 0
+#define RYOLO_IOU_MODE_GIOU 1
+/* out[i] = iou(a_i, b_i), i < n  (the reference's N-vs-N form) */
+int ryolo_riou_paired(const float* a, const float* b, int n, int stride_a, int stride_b, int mode,
+                      float* out, void* stream);
+/* out[i*m + j] = iou(a_i, b_j)  (the reference's 1-vs-N form applied to every row of a) */
+int ryolo_riou_pairwise(const float* a, int n, int stride_a, const float* b, int m, int stride_b,
+                        int mode, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * non_max_suppression candidate filter (reference: utils/nms/nms.py:34-40, 55)
+ *
+ * pred [p, 6+nc] fp32 (x,y,w,h,theta,obj, cls...), one image.  Exactly like the reference:
+ * class_conf/class_pred = max/argmax over the class columns (first max on ties), pred[:,5] *=
+ * class_conf IN PLACE (nms.py:35), keep rows with conf > conf_thres, w > min_wh, h > min_wh and
+ * all 6+nc values finite.  Survivors are written in input order to out [*, 8] =
+ * (x,y,w,h,theta,conf,class_conf,class) and counted in num_out (device int32[1]).
+ * Stable (order-preserving) compaction; capacity = max rows `out` can hold (extra rows dropped,
+ * num_out still reports the true count so that the caller can detect overflow).
+ * ------------------------------------------------------------------------------------------ */
+size_t ryolo_nms_filter_workspace_bytes(int p);
+int ryolo_nms_filter(float* pred, int p, int nc, float conf_thres, float min_wh, float* out,
+                     int capacity, int32_t* num_out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * YOLO head decode (reference: YOLOLayer.forward eval branch, model/models.py:198-227)
+ *
+ * p        [bs, na*(nc+6), ny, nx] fp32 NCHW raw head output (the conv's natural layout).
+ * anchors  [na, 3] fp32 (w_px, h_px, theta): anchor_vec = (w/stride, h/stride, theta)
+ *          (model/model_utils.py:30-32).
+ * io_out   [bs, io_rows_total, nc+6] fp32; this layer writes rows [row_offset, row_offset+na*ny*nx)
+ *          of every image, in the reference's (a, y, x) order, so the three layers concatenate
+ *          by row_offset exactly like torch.cat(io, 1) (model/models.py:298).
+ * p_out    optional [bs, na, ny, nx, nc+6] fp32 permuted raw copy (the second tensor the
+ *          reference returns); may be NULL.
+ * arc_default != 0 -> sigmoid on obj and class columns ('default' arcs); nc == 1 forces the
+ * class column to 1 (models.py:220-221).
+ * ------------------------------------------------------------------------------------------ */
+int ryolo_yolo_decode(const float* p, int bs, int na, int nc, int ny, int nx, const float* anchors,
+                      float stride, float context_factor, int arc_default, float* io_out,
+                      int io_rows_total, int row_offset, float* p_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RYOLO_H_ */

@@ -1,0 +1,228 @@
+// libryolo.so: error/launch bookkeeping, the non_max_suppression candidate filter and the YOLO head decode.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace ryolo {
+
+std::atomic<uint64_t> g_launches{0};
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+void set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// non_max_suppression candidate filter (reference utils/nms/nms.py:34-40,55)
+// ------------------------------------------------------------------------------------------------
+constexpr int FT = 256;  // rows per block
+
+// class_conf, class_pred = pred[:, 6:].max(1)  (first maximum on ties; NaN propagates like torch.max)
+__device__ __forceinline__ void class_max(const float* __restrict__ row, int nc, float* best_out, int* idx_out,
+                                          bool* finite_out) {
+  float best = row[6];
+  int bi = 0;
+  bool fin = isfinite(best);
+  for (int k = 1; k < nc; k++) {
+    const float v = row[6 + k];
+    fin = fin && isfinite(v);
+    if (v > best || (v != v && best == best)) { best = v; bi = k; }
+  }
+  *best_out = best; *idx_out = bi; *finite_out = fin;
+}
+
+// (pred[:, 5] > conf_thres) & (pred[:, 2:4] > min_wh).all(1) & torch.isfinite(pred).all(1)   (nms.py:40)
+__device__ __forceinline__ bool keep_row(const float* __restrict__ row, float conf, bool cls_finite, float conf_thres,
+                                         float min_wh) {
+  bool fin = cls_finite && isfinite(conf);
+#pragma unroll
+  for (int k = 0; k < 5; k++) fin = fin && isfinite(row[k]);
+  return conf > conf_thres && row[2] > min_wh && row[3] > min_wh && fin;
+}
+
+// pass 1: in-place conf update + per-block survivor counts
+__global__ void __launch_bounds__(FT) nms_filter_count_kernel(float* __restrict__ pred, int p, int nc, float conf_thres,
+                                                             float min_wh, int* __restrict__ block_counts) {
+  const int i = blockIdx.x * FT + threadIdx.x;
+  bool keep = false;
+  if (i < p) {
+    float* row = pred + (size_t)i * (6 + nc);
+    float best; int bi; bool fin;
+    class_max(row, nc, &best, &bi, &fin);
+    const float conf = row[5] * best;  // pred[:, 5] *= class_conf, in place (nms.py:35)
+    row[5] = conf;
+    keep = keep_row(row, conf, fin, conf_thres, min_wh);
+  }
+  const int cnt = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
+}
+
+// pass 2: exclusive scan of the block counts (single CTA), total -> num_out
+__global__ void __launch_bounds__(1024) nms_filter_scan_kernel(int* __restrict__ block_counts, int nblocks,
+                                                               int* __restrict__ num_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int start = 0; start < nblocks; start += 1024) {
+    const int i = start + tid;
+    const int v = i < nblocks ? block_counts[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int incl = x + (warp ? s_warp[warp - 1] : 0) + carry;
+    if (i < nblocks) block_counts[i] = incl - v;  // exclusive
+    __syncthreads();
+    if (tid == 1023) s_carry = incl;
+    __syncthreads();
+  }
+  if (tid == 0) *num_out = s_carry;
+}
+
+// pass 3: stable write of the survivors
+__global__ void __launch_bounds__(FT) nms_filter_write_kernel(const float* __restrict__ pred, int p, int nc,
+                                                             float conf_thres, float min_wh,
+                                                             const int* __restrict__ block_offsets,
+                                                             float* __restrict__ out, int capacity) {
+  __shared__ int s_warp[FT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x * FT + tid;
+  bool keep = false;
+  float cc = 0.f, ci = 0.f;
+  const float* row = pred + (size_t)i * (6 + nc);
+  if (i < p) {  // pass 1 already stored conf in row[5]
+    float best; int bi; bool fin;
+    class_max(row, nc, &best, &bi, &fin);
+    cc = best; ci = (float)bi;
+    keep = keep_row(row, row[5], fin, conf_thres, min_wh);
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  int prefix = 0;
+  for (int w = 0; w < warp; w++) prefix += s_warp[w];
+  if (keep) {
+    const int dst = block_offsets[blockIdx.x] + prefix + __popc(bal & ((1u << lane) - 1u));
+    if (dst < capacity) {
+      float* o = out + (size_t)dst * 8;
+      o[0] = row[0]; o[1] = row[1]; o[2] = row[2]; o[3] = row[3]; o[4] = row[4];
+      o[5] = row[5]; o[6] = cc; o[7] = ci;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// YOLO head decode (reference model/models.py:198-227)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ p, int bs, int na, int nc, int ny,
+                                                          int nx, const float* __restrict__ anchors, float stride,
+                                                          float ctx, int arc_default, float* __restrict__ io,
+                                                          int rows_total, int row_offset, float* __restrict__ p_out) {
+  const int no = nc + 6;
+  const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over bs*na*ny*nx
+  const size_t total = (size_t)bs * na * ny * nx;
+  if (cell >= total) return;
+  const int x = (int)(cell % nx);
+  const int y = (int)((cell / nx) % ny);
+  const int a = (int)((cell / ((size_t)nx * ny)) % na);
+  const int b = (int)(cell / ((size_t)nx * ny * na));
+  const size_t plane = (size_t)ny * nx;
+  const float* src = p + ((size_t)b * na * no + (size_t)a * no) * plane + (size_t)y * nx + x;
+  float* dst = io + ((size_t)b * rows_total + row_offset + ((size_t)a * ny + y) * nx + x) * no;
+  float* pd = p_out ? p_out + cell * no : nullptr;
+  // anchor_vec = anchors / stride (model_utils.py:30-31), theta untouched
+  const float aw = anchors[a * 3 + 0] / stride, ah = anchors[a * 3 + 1] / stride, at = anchors[a * 3 + 2];
+  const float t0 = src[0], t1 = src[plane], t2 = src[2 * plane], t3 = src[3 * plane], t4 = src[4 * plane];
+  if (pd) { pd[0] = t0; pd[1] = t1; pd[2] = t2; pd[3] = t3; pd[4] = t4; }
+  float bx = (1.f / (1.f + expf(-t0)) + (float)x) * stride;   // (sigmoid + grid) * stride
+  float by = (1.f / (1.f + expf(-t1)) + (float)y) * stride;
+  float bw = (expf(t2) * aw) * stride;
+  float bh = (expf(t3) * ah) * stride;
+  const float th = atanf(t4) + at;
+  bh = bh / ctx;                    // io[..., 3] /= context_factor
+  bw = bw - bh * (ctx - 1.f);       // io[..., 2] -= io[..., 3] * (context_factor - 1)
+  dst[0] = bx; dst[1] = by; dst[2] = bw; dst[3] = bh; dst[4] = th;
+  for (int k = 5; k < no; k++) {
+    const float v = src[(size_t)k * plane];
+    if (pd) pd[k] = v;
+    float o = arc_default ? 1.f / (1.f + expf(-v)) : v;
+    if (nc == 1 && k == 6) o = 1.f;  // models.py:220-221
+    dst[k] = o;
+  }
+}
+
+}  // namespace ryolo
+
+using namespace ryolo;
+
+extern "C" int ryolo_abi_version(void) { return 1; }
+extern "C" const char* ryolo_last_error(void) { return err_buf(); }
+extern "C" uint64_t ryolo_launch_count(void) { return g_launches.load(); }
+
+extern "C" size_t ryolo_nms_filter_workspace_bytes(int p) {
+  const int nblocks = (p > 0 ? p : 0) / FT + 1;
+  return align_up((size_t)nblocks * sizeof(int), 256) + 256;
+}
+
+extern "C" int ryolo_nms_filter(float* pred, int p, int nc, float conf_thres, float min_wh, float* out, int capacity,
+                                int32_t* num_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(p >= 0 && nc >= 1 && capacity >= 0 && num_out != nullptr);
+  if (p == 0) {
+    RYOLO_CUDA_TRY(cudaMemsetAsync(num_out, 0, sizeof(int32_t), stream));
+    return RYOLO_OK;
+  }
+  RYOLO_ARG_CHECK(pred && out && workspace);
+  if (workspace_bytes < ryolo_nms_filter_workspace_bytes(p)) {
+    set_err("ryolo_nms_filter: workspace too small");
+    return RYOLO_E_WORKSPACE;
+  }
+  const int nblocks = (p + FT - 1) / FT;
+  int* counts = static_cast<int*>(workspace);
+  nms_filter_count_kernel<<<nblocks, FT, 0, stream>>>(pred, p, nc, conf_thres, min_wh, counts);
+  RYOLO_LAUNCH_CHECK();
+  nms_filter_scan_kernel<<<1, 1024, 0, stream>>>(counts, nblocks, num_out);
+  RYOLO_LAUNCH_CHECK();
+  nms_filter_write_kernel<<<nblocks, FT, 0, stream>>>(pred, p, nc, conf_thres, min_wh, counts, out, capacity);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_yolo_decode(const float* p, int bs, int na, int nc, int ny, int nx, const float* anchors,
+                                 float stride, float context_factor, int arc_default, float* io_out, int io_rows_total,
+                                 int row_offset, float* p_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(bs >= 0 && na > 0 && nc >= 1 && ny > 0 && nx > 0);
+  RYOLO_ARG_CHECK(p && anchors && io_out);
+  RYOLO_ARG_CHECK(row_offset >= 0 && row_offset + na * ny * nx <= io_rows_total);
+  const size_t total = (size_t)bs * na * ny * nx;
+  if (total == 0) return RYOLO_OK;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  yolo_decode_kernel<<<blocks, 256, 0, stream>>>(p, bs, na, nc, ny, nx, anchors, stride, context_factor, arc_default,
+                                                 io_out, io_rows_total, row_offset, p_out);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}

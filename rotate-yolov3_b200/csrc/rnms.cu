@@ -1,0 +1,425 @@
+// Rotated NMS for sm_100a: device sort -> per-box geometry -> upper-triangle suppression mask
+// (conservative filter + pinned-arithmetic exact overlap on the survivors) -> on-device greedy scan
+// -> ascending compaction of the kept ORIGINAL indices.  No host round trip anywhere.
+//
+// Replaces r_nms / nms_cuda of the reference (utils/nms/src/rotate_polygon_nms.cpp:7-16,
+// utils/nms/src/rotate_polygon_nms_kernel.cu:323-384).  Differences in *how* (never in the result):
+//   * only tiles with column-block >= row-block are evaluated (the reference evaluates all N^2
+//     pairs because its early exit is commented out, :267, yet its host scan reads only those, :371-374);
+//   * 2 sincos per BOX instead of per PAIR (prep kernel), identical values;
+//   * a conservative separating-axis pre-filter rejects pairs whose exact result is provably
+//     "0 candidate points -> area 0 -> IoU 0" ("filter soundness"); survivors are compacted
+//     through a shared-memory queue so the ~1k-instruction exact path runs with full warps;
+//   * the 50 MB mask never leaves HBM: the greedy scan runs on the device.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/util_type.cuh>
+
+#include "common.cuh"
+#include "rbox_exact.cuh"
+
+namespace ryolo {
+
+typedef unsigned long long u64;
+
+constexpr int TB = 64;            // boxes per tile side == bits per mask word (reference threadsPerBlock, :20)
+constexpr int CH = 8;             // column blocks handled per CTA
+constexpr int MASK_THREADS = 256;
+constexpr int SCAN_THREADS = 1024;
+
+// field indices of the SoA geometry array geom[f * n_pad + i]
+enum {
+  F_PX = 0, F_PY = 4, F_ABX = 8, F_ABY = 9, F_ADX = 10, F_ADY = 11, F_ABAB = 12, F_ADAD = 13,
+  F_W = 14, F_H = 15, F_AREA = 16, F_CX = 17, F_CY = 18, F_RAD = 19, F_UX = 20, F_UY = 21,
+  F_HW = 22, F_HH = 23
+};
+
+__global__ void rnms_keys_kernel(const float* __restrict__ dets, int n, float* __restrict__ keys,
+                                 int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = dets[(size_t)i * 6 + 5];
+    vals[i] = i;
+  }
+}
+
+// One thread per score-sorted box: gather, pinned corner arithmetic, filter data.
+__global__ void rnms_prep_kernel(const float* __restrict__ dets, const int* __restrict__ order_in, int n,
+                                 int n_pad, float* __restrict__ sorted_boxes, int* __restrict__ order_out,
+                                 float* __restrict__ geom, unsigned char* __restrict__ keep_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  float g[kGeomFields];
+#pragma unroll
+  for (int f = 0; f < kGeomFields; f++) g[f] = 0.f;
+  if (i < n) {
+    const int src = order_in[i];
+    order_out[i] = src;
+    keep_flag[i] = 0;
+    float b[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      b[k] = dets[(size_t)src * 6 + k];
+      sorted_boxes[(size_t)i * 6 + k] = b[k];
+    }
+    const float cx = b[0], cy = b[1], w = b[2], h = b[3], ang = b[4];
+    float px[4], py[4], c, s;
+    exact_corners(cx, cy, w, h, ang, px, py, &c, &s);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      g[F_PX + k] = px[k];
+      g[F_PY + k] = py[k];
+    }
+    // in_rect invariants (:143-155): ab = P1 - P0, ad = P3 - P0
+    const float abx = __fsub_rn(px[1], px[0]), aby = __fsub_rn(py[1], py[0]);
+    const float adx = __fsub_rn(px[3], px[0]), ady = __fsub_rn(py[3], py[0]);
+    g[F_ABX] = abx; g[F_ABY] = aby; g[F_ADX] = adx; g[F_ADY] = ady;
+    g[F_ABAB] = __fmaf_rn(abx, abx, __fmul_rn(aby, aby));
+    g[F_ADAD] = __fmaf_rn(adx, adx, __fmul_rn(ady, ady));
+    g[F_W] = w; g[F_H] = h;
+    g[F_AREA] = __fmul_rn(w, h);
+    // conservative filter data: only for well-conditioned boxes, else "never reject"
+    const float mag = fabsf(cx) + fabsf(cy) + fmaxf(fabsf(w), fabsf(h));
+    const bool ok = isfinite(cx) && isfinite(cy) && isfinite(w) && isfinite(h) && isfinite(ang) && w > 0.f &&
+                    h > 0.f && fminf(w, h) >= 2.5e-4f * mag;
+    const float inf = __int_as_float(0x7f800000);
+    const float pad = 2e-3f * 0.5f * (w + h) + 1e-5f * mag;
+    g[F_CX] = cx; g[F_CY] = cy;
+    g[F_UX] = c; g[F_UY] = s;
+    g[F_HW] = ok ? 0.5f * w + pad : inf;
+    g[F_HH] = ok ? 0.5f * h + pad : inf;
+    g[F_RAD] = ok ? 0.5f * sqrtf(w * w + h * h) * 1.002f + pad : inf;
+  }
+#pragma unroll
+  for (int f = 0; f < kGeomFields; f++) geom[(size_t)f * n_pad + i] = g[f];
+}
+
+struct TileGeom {  // accessor over a shared-memory SoA tile [kGeomFields][TB]
+  const float* t;
+  int i;
+  __device__ __forceinline__ float f(int field) const { return t[field * TB + i]; }
+  __device__ __forceinline__ float px(int k) const { return f(F_PX + k); }
+  __device__ __forceinline__ float py(int k) const { return f(F_PY + k); }
+  __device__ __forceinline__ float abx() const { return f(F_ABX); }
+  __device__ __forceinline__ float aby() const { return f(F_ABY); }
+  __device__ __forceinline__ float adx() const { return f(F_ADX); }
+  __device__ __forceinline__ float ady() const { return f(F_ADY); }
+  __device__ __forceinline__ float abab() const { return f(F_ABAB); }
+  __device__ __forceinline__ float adad() const { return f(F_ADAD); }
+};
+
+struct MaskSmem {
+  float row[kGeomFields * TB];
+  float col[kGeomFields * TB];
+  float scratch[3 * kMaxPts * MASK_THREADS];
+  u64 mask[TB * CH];
+  unsigned short queue[TB * TB];
+  int cnt;
+};
+
+// Conservative "provably no intersection" test.  true => the exact path would find 0 candidate
+// points (so IoU == 0 exactly); false => unknown, run the exact path.  NaN/inf anywhere => false.
+__device__ __forceinline__ bool surely_disjoint(float rcx, float rcy, float rrad, float rux, float ruy, float rhw,
+                                                float rhh, float ccx, float ccy, float crad, float cux, float cuy,
+                                                float chw, float chh) {
+  const float dx = ccx - rcx, dy = ccy - rcy;
+  const float R = rrad + crad;
+  if (dx * dx + dy * dy > R * R) return true;
+  const float C = fabsf(rux * cux + ruy * cuy);
+  const float S = fabsf(rux * cuy - ruy * cux);
+  if (fabsf(dx * rux + dy * ruy) > rhw + chw * C + chh * S) return true;
+  if (fabsf(dy * rux - dx * ruy) > rhh + chw * S + chh * C) return true;
+  if (fabsf(dx * cux + dy * cuy) > chw + rhw * C + rhh * S) return true;
+  if (fabsf(dy * cux - dx * cuy) > chh + rhw * S + rhh * C) return true;
+  return false;
+}
+
+__global__ void __launch_bounds__(MASK_THREADS) rnms_mask_kernel(const float* __restrict__ geom, int n, int n_pad,
+                                                                 int col_blocks, float thr, int use_filter,
+                                                                 u64* __restrict__ mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MaskSmem& sm = *reinterpret_cast<MaskSmem*>(smem_raw);
+  const int rb = blockIdx.y;
+  const int cb0 = rb + blockIdx.x * CH;
+  if (cb0 >= col_blocks) return;
+  const int ncols = min(CH, col_blocks - cb0);
+  const int tid = threadIdx.x;
+
+  for (int e = tid; e < kGeomFields * TB; e += MASK_THREADS) {
+    const int f = e / TB, i = e % TB;
+    sm.row[e] = geom[(size_t)f * n_pad + rb * TB + i];
+  }
+  for (int e = tid; e < TB * CH; e += MASK_THREADS) sm.mask[e] = 0ull;
+
+  const int r = tid & (TB - 1);
+  const int g = tid >> 6;  // 4 groups of 16 columns
+  const int lane = tid & 31;
+
+  for (int cc = 0; cc < ncols; cc++) {
+    const int cbi = cb0 + cc;
+    __syncthreads();  // previous tile fully consumed (also covers the row-tile load on cc == 0)
+    for (int e = tid; e < kGeomFields * TB; e += MASK_THREADS) {
+      const int f = e / TB, i = e % TB;
+      sm.col[e] = geom[(size_t)f * n_pad + cbi * TB + i];
+    }
+    if (tid == 0) sm.cnt = 0;
+    __syncthreads();
+
+    // ---- phase A: filter, compact survivors into the queue ----
+    {
+      const float rcx = sm.row[F_CX * TB + r], rcy = sm.row[F_CY * TB + r], rrad = sm.row[F_RAD * TB + r];
+      const float rux = sm.row[F_UX * TB + r], ruy = sm.row[F_UY * TB + r];
+      const float rhw = sm.row[F_HW * TB + r], rhh = sm.row[F_HH * TB + r];
+      const bool row_ok = rb * TB + r < n;
+#pragma unroll 4
+      for (int k = 0; k < 16; k++) {
+        const int c = g * 16 + k;
+        bool cand = row_ok && (cbi * TB + c < n) && (cbi > rb || c > r);
+        if (cand && use_filter) {
+          cand = !surely_disjoint(rcx, rcy, rrad, rux, ruy, rhw, rhh, sm.col[F_CX * TB + c], sm.col[F_CY * TB + c],
+                                  sm.col[F_RAD * TB + c], sm.col[F_UX * TB + c], sm.col[F_UY * TB + c],
+                                  sm.col[F_HW * TB + c], sm.col[F_HH * TB + c]);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&sm.cnt, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (cand) sm.queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)((r << 6) | c);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase B: exact overlap on the survivors, one pair per thread ----
+    {
+      const int cnt = sm.cnt;
+      PtScratch sc;
+      sc.x = sm.scratch + tid;
+      sc.y = sm.scratch + kMaxPts * MASK_THREADS + tid;
+      sc.k = sm.scratch + 2 * kMaxPts * MASK_THREADS + tid;
+      sc.stride = MASK_THREADS;
+      for (int q = tid; q < cnt; q += MASK_THREADS) {
+        const int e = sm.queue[q];
+        const int qr = e >> 6, qc = e & 63;
+        TileGeom g1{sm.row, qr}, g2{sm.col, qc};
+        const float inter = exact_inter_area(g1, g2, sc);
+        const float iou = exact_iou_from_inter(g1.f(F_AREA), g2.f(F_W), g2.f(F_H), inter);
+        if (iou > thr) atomicOr(&sm.mask[qr * CH + cc], 1ull << qc);
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < TB * ncols; e += MASK_THREADS) {
+    const int rr = e / ncols, cc = e % ncols;
+    const int row = rb * TB + rr;
+    if (row < n) mask[(size_t)row * col_blocks + cb0 + cc] = sm.mask[rr * CH + cc];
+  }
+}
+
+// Greedy scan (reference host loop :358-376) + original-index compaction (:380-383), one CTA.
+__global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __restrict__ mask, int n, int col_blocks,
+                                                                 const int* __restrict__ order,
+                                                                 unsigned char* __restrict__ keep_flag,
+                                                                 long long* __restrict__ keep_out,
+                                                                 int* __restrict__ num_keep) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* remv = reinterpret_cast<u64*>(smem_raw);  // [col_blocks]
+  __shared__ u64 s_kept;
+  __shared__ int s_warp_sums[SCAN_THREADS / 32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = tid; j < col_blocks; j += SCAN_THREADS) remv[j] = 0ull;
+  __syncthreads();
+
+  for (int b = 0; b < col_blocks; b++) {
+    if (warp == 0) {
+      const int row0 = b * TB + lane, row1 = row0 + 32;
+      const u64 d0 = row0 < n ? mask[(size_t)row0 * col_blocks + b] : 0ull;
+      const u64 d1 = row1 < n ? mask[(size_t)row1 * col_blocks + b] : 0ull;
+      u64 rm = remv[b];
+      u64 kept = 0ull;
+      const int nvalid = min(TB, n - b * TB);
+      for (int i = 0; i < nvalid; i++) {
+        const u64 di = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
+        if (!((rm >> i) & 1ull)) {
+          kept |= 1ull << i;
+          rm |= di;
+        }
+      }
+      if (lane == 0) s_kept = kept;
+      // mark kept boxes by ORIGINAL index
+      if ((kept >> lane) & 1ull) keep_flag[order[b * TB + lane]] = 1;
+      if ((kept >> (lane + 32)) & 1ull) keep_flag[order[b * TB + 32 + lane]] = 1;
+    }
+    __syncthreads();
+    const u64 kept = s_kept;
+    // every later column word: OR in the rows of the boxes kept in this block
+    for (int j = b + 1 + tid; j < col_blocks; j += SCAN_THREADS) {
+      u64 acc = 0ull;
+      u64 bits = kept;
+      const u64* base = mask + (size_t)b * TB * col_blocks + j;
+      while (bits) {
+        // up to 4 independent loads in flight
+        u64 v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        int i0 = __ffsll((long long)bits) - 1; bits &= bits - 1;
+        v0 = base[(size_t)i0 * col_blocks];
+        if (bits) { int i1 = __ffsll((long long)bits) - 1; bits &= bits - 1; v1 = base[(size_t)i1 * col_blocks]; }
+        if (bits) { int i2 = __ffsll((long long)bits) - 1; bits &= bits - 1; v2 = base[(size_t)i2 * col_blocks]; }
+        if (bits) { int i3 = __ffsll((long long)bits) - 1; bits &= bits - 1; v3 = base[(size_t)i3 * col_blocks]; }
+        acc |= (v0 | v1) | (v2 | v3);
+      }
+      remv[j] |= acc;
+    }
+    __syncthreads();
+  }
+
+  // compaction over ORIGINAL indices, ascending
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += SCAN_THREADS) {
+    const int i = start + tid;
+    const int flag = (i < n) ? (int)keep_flag[i] : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp_sums[warp] = __popc(bal);
+    __syncthreads();
+    int prefix = 0;
+    for (int w = 0; w < warp; w++) prefix += s_warp_sums[w];
+    const int base = s_base;
+    if (flag) keep_out[base + prefix + __popc(bal & ((1u << lane) - 1u))] = (long long)i;
+    __syncthreads();
+    if (tid == SCAN_THREADS - 1) s_base = base + prefix + __popc(bal);
+    __syncthreads();
+  }
+  if (tid == 0) *num_keep = s_base;
+}
+
+struct RnmsPlan {
+  int n, n_pad, col_blocks;
+  size_t cub_bytes;
+  // offsets
+  float* sorted_boxes;
+  int* order;
+  float* keys[2];
+  int* vals[2];
+  float* geom;
+  u64* mask;
+  unsigned char* keep_flag;
+  void* cub_temp;
+  size_t total;
+};
+
+static size_t cub_temp_bytes(int n) {
+  size_t bytes = 0;
+  cub::DoubleBuffer<float> k(nullptr, nullptr);
+  cub::DoubleBuffer<int> v(nullptr, nullptr);
+  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, k, v, n, 0, 32, (cudaStream_t)0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear (no device in this process: size-only query)
+    bytes = 0;
+  }
+  // conservative floor so that a size computed on a GPU-less host still fits the real query
+  const size_t floor_bytes = (size_t)1 << 20;
+  return bytes > floor_bytes ? bytes : floor_bytes + (size_t)16 * (size_t)(n > 0 ? n : 0);
+}
+
+static void plan_rnms(int n, void* ws, RnmsPlan* p) {
+  p->n = n;
+  p->n_pad = (n + TB - 1) / TB * TB;
+  p->col_blocks = (n + TB - 1) / TB;
+  p->cub_bytes = cub_temp_bytes(n);
+  Carver c(ws);
+  p->sorted_boxes = c.take<float>((size_t)n * 6);
+  p->order = c.take<int>(n);
+  p->keys[0] = c.take<float>(n);
+  p->keys[1] = c.take<float>(n);
+  p->vals[0] = c.take<int>(n);
+  p->vals[1] = c.take<int>(n);
+  p->geom = c.take<float>((size_t)kGeomFields * p->n_pad);
+  p->mask = c.take<u64>((size_t)n * p->col_blocks);
+  p->keep_flag = c.take<unsigned char>(n);
+  p->cub_temp = c.take<unsigned char>(p->cub_bytes);
+  p->total = align_up(c.off, 256);
+}
+
+}  // namespace ryolo
+
+using namespace ryolo;
+
+extern "C" size_t ryolo_rnms_workspace_bytes(int n) {
+  if (n <= 0) return 256;
+  RnmsPlan p;
+  plan_rnms(n, nullptr, &p);
+  return p.total;
+}
+
+extern "C" int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(n >= 0);
+  RYOLO_ARG_CHECK(num_keep != nullptr);
+  if (n == 0) {
+    RYOLO_CUDA_TRY(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), stream));
+    return RYOLO_OK;
+  }
+  RYOLO_ARG_CHECK(dets != nullptr && keep_out != nullptr && workspace != nullptr);
+  RYOLO_ARG_CHECK((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  RnmsPlan p;
+  plan_rnms(n, workspace, &p);
+  if (p.total > workspace_bytes) {
+    set_err("ryolo_rnms: workspace %zu B < required %zu B", workspace_bytes, p.total);
+    return RYOLO_E_WORKSPACE;
+  }
+  const int T = 256;
+  rnms_keys_kernel<<<(n + T - 1) / T, T, 0, stream>>>(dets, n, p.keys[0], p.vals[0]);
+  RYOLO_LAUNCH_CHECK();
+  cub::DoubleBuffer<float> dk(p.keys[0], p.keys[1]);
+  cub::DoubleBuffer<int> dv(p.vals[0], p.vals[1]);
+  size_t need = 0;
+  RYOLO_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, dk, dv, n, 0, 32, stream));
+  if (need > p.cub_bytes) {
+    set_err("ryolo_rnms: sort scratch %zu B > planned %zu B", need, p.cub_bytes);
+    return RYOLO_E_WORKSPACE;
+  }
+  size_t tmp = p.cub_bytes;
+  RYOLO_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(p.cub_temp, tmp, dk, dv, n, 0, 32, stream));
+  count_launch(4);  // radix sort passes (library kernels, counted as a lower bound)
+  rnms_prep_kernel<<<(p.n_pad + T - 1) / T, T, 0, stream>>>(dets, dv.Current(), n, p.n_pad, p.sorted_boxes, p.order,
+                                                            p.geom, p.keep_flag);
+  RYOLO_LAUNCH_CHECK();
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      RYOLO_CUDA_TRY(cudaFuncSetAttribute(rnms_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(MaskSmem)));
+      attr_set = true;
+    }
+    dim3 grid((p.col_blocks + CH - 1) / CH, p.col_blocks);
+    rnms_mask_kernel<<<grid, MASK_THREADS, sizeof(MaskSmem), stream>>>(p.geom, n, p.n_pad, p.col_blocks, thr,
+                                                                        thr >= 0.f ? 1 : 0, p.mask);
+    RYOLO_LAUNCH_CHECK();
+  }
+  {
+    const size_t smem = (size_t)p.col_blocks * sizeof(u64);
+    if (smem > 200 * 1024) {
+      set_err("ryolo_rnms: n=%d too large for the single-CTA scan (col_blocks=%d)", n, p.col_blocks);
+      return RYOLO_E_UNSUPPORTED;
+    }
+    if (smem > 40 * 1024)
+      RYOLO_CUDA_TRY(cudaFuncSetAttribute(rnms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rnms_scan_kernel<<<1, SCAN_THREADS, smem, stream>>>(p.mask, n, p.col_blocks, p.order, p.keep_flag,
+                                                        reinterpret_cast<long long*>(keep_out), num_keep);
+    RYOLO_LAUNCH_CHECK();
+  }
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_rnms_debug_views(void* workspace, int n, const float** sorted_boxes, const int32_t** order,
+                                      const unsigned long long** mask) {
+  RYOLO_ARG_CHECK(workspace != nullptr && n > 0);
+  RnmsPlan p;
+  plan_rnms(n, workspace, &p);
+  if (sorted_boxes) *sorted_boxes = p.sorted_boxes;
+  if (order) *order = p.order;
+  if (mask) *mask = p.mask;
+  return RYOLO_OK;
+}

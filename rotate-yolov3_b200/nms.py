@@ -1,0 +1,114 @@
+"""Rotated NMS behind the reference's Python signatures.
+
+* ``r_nms(dets, threshold)``            <- utils/nms/src/rotate_polygon_nms.cpp:7-16 (pybind module ``r_nms``)
+* ``non_max_suppression(prediction, conf_thres, nms_thres)`` <- utils/nms/nms.py:4-69 (the ``use_cuda_nms`` branch)
+
+Everything below the tensor plumbing happens in libryolo.so (ryolo_rnms / ryolo_nms_filter)."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _workspace(nbytes, device):
+    # torch's caching allocator is stream-aware; 256-B alignment is guaranteed (512-B blocks)
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def r_nms(dets, threshold):
+    """dets: Tensor[N, 6] float32 CUDA (x, y, w, h, theta, score) -> Tensor[K] int64 of kept ORIGINAL indices,
+    ascending (utils/nms/src/rotate_polygon_nms_kernel.cu:380-383).
+
+    Reference behaviours kept: a non-CUDA input raises RuntimeError (CHECK_CUDA, rotate_polygon_nms.cpp:3,8);
+    an empty input returns an empty CPU long tensor (:9-10); the call is synchronous."""
+    if not isinstance(dets, torch.Tensor) or not dets.is_cuda:
+        raise RuntimeError("dets must be a CUDAtensor ")
+    if dets.numel() == 0:
+        return torch.empty((0,), dtype=torch.long, device="cpu")
+    if dets.dim() != 2 or dets.shape[1] < 6:
+        raise RuntimeError("r_nms: dets must be [N, 6] (x, y, w, h, theta, score)")
+    with torch.cuda.device(dets.device):
+        d = dets[:, :6].to(torch.float32).contiguous()
+        n = d.shape[0]
+        ws_bytes = _lib.lib.ryolo_rnms_workspace_bytes(n)
+        ws = _workspace(ws_bytes, d.device)
+        keep = torch.empty((n,), dtype=torch.long, device=d.device)
+        num = torch.empty((1,), dtype=torch.int32, device=d.device)
+        st = _lib.lib.ryolo_rnms(_lib.ptr(d), n, float(threshold), _lib.ptr(keep), _lib.ptr(num), _lib.ptr(ws),
+                                 ws_bytes, _lib.stream_ptr(d.device))
+        _lib.check(st, "ryolo_rnms")
+        k = int(num.item())  # the reference is synchronous too (blocking D2H of the whole mask)
+        return keep[:k]
+
+
+def rnms_debug(dets, threshold):
+    """Test hook: run r_nms and also return (sorted_boxes [N,6], order [N] int32, mask [N, ceil(N/64)] int64 view)."""
+    d = dets[:, :6].to(torch.float32).contiguous()
+    n = d.shape[0]
+    with torch.cuda.device(d.device):
+        ws_bytes = _lib.lib.ryolo_rnms_workspace_bytes(n)
+        ws = _workspace(ws_bytes, d.device)
+        keep = torch.empty((n,), dtype=torch.long, device=d.device)
+        num = torch.empty((1,), dtype=torch.int32, device=d.device)
+        st = _lib.lib.ryolo_rnms(_lib.ptr(d), n, float(threshold), _lib.ptr(keep), _lib.ptr(num), _lib.ptr(ws),
+                                 ws_bytes, _lib.stream_ptr(d.device))
+        _lib.check(st, "ryolo_rnms")
+        k = int(num.item())
+        pb, po, pm = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(_lib.lib.ryolo_rnms_debug_views(_lib.ptr(ws), n, ctypes.byref(pb), ctypes.byref(po),
+                                                   ctypes.byref(pm)), "ryolo_rnms_debug_views")
+        base = ws.data_ptr()
+        cb = (n + 63) // 64
+
+        def view(p, nbytes, dtype, shape):
+            off = p.value - base
+            return ws[off:off + nbytes].view(dtype).view(shape).clone()
+        boxes = view(pb, n * 6 * 4, torch.float32, (n, 6))
+        order = view(po, n * 4, torch.int32, (n,))
+        mask = view(pm, n * cb * 8, torch.int64, (n, cb))
+        return keep[:k].clone(), boxes, order, mask
+
+
+def nms_filter(pred, conf_thres, min_wh=2.0):
+    """Candidate filter of non_max_suppression for ONE image (utils/nms/nms.py:34-40,55).
+    pred [P, 6+nc] float32 CUDA, modified in place (pred[:, 5] *= class_conf).  Returns Tensor[n, 8]
+    (x, y, w, h, theta, conf, class_conf, class) in input order."""
+    assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous()
+    p, no = pred.shape
+    nc = no - 6
+    with torch.cuda.device(pred.device):
+        out = torch.empty((p, 8), dtype=torch.float32, device=pred.device)
+        num = torch.empty((1,), dtype=torch.int32, device=pred.device)
+        ws_bytes = _lib.lib.ryolo_nms_filter_workspace_bytes(p)
+        ws = _workspace(ws_bytes, pred.device)
+        st = _lib.lib.ryolo_nms_filter(_lib.ptr(pred), p, nc, float(conf_thres), float(min_wh), _lib.ptr(out), p,
+                                       _lib.ptr(num), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(pred.device))
+        _lib.check(st, "ryolo_nms_filter")
+        return out[:int(num.item())]
+
+
+def non_max_suppression(prediction, conf_thres=0.5, nms_thres=0.5):
+    """Drop-in for utils/nms/nms.py:4-69: per image, (x, y, w, h, a, object_conf*class_conf, class_conf, class)
+    rows of the survivors sorted by confidence, or None.  Mutates prediction[..., 5] like the reference (:35)."""
+    min_wh = 2
+    output = [None] * len(prediction)
+    for image_i, pred in enumerate(prediction):
+        if prediction.numel() == 0:
+            continue
+        if not pred.is_contiguous():  # keep the in-place side effect on the caller's tensor
+            raise RuntimeError("non_max_suppression: prediction must be contiguous")
+        cand = nms_filter(pred, conf_thres, min_wh)
+        if len(cand) == 0:
+            continue
+        cand = cand[(-cand[:, 5]).argsort()]
+        det_max = []
+        for c in cand[:, -1].unique():
+            dc = cand[cand[:, -1] == c]
+            dc = dc[(-dc[:, 5]).argsort()]
+            inds = r_nms(dc[:, :6], nms_thres)
+            det_max.append(dc[inds])
+        if len(det_max):
+            det_max = torch.cat(det_max)
+            output[image_i] = det_max[(-det_max[:, 5]).argsort()]
+    return output

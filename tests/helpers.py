@@ -1,0 +1,109 @@
+"""Test-side helpers: oracle / reference-build loaders and the seeded input generators of SURVEY.md 8(d).
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/ -- never the product."""
+import ctypes
+import math
+import os
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+FP = ctypes.POINTER(ctypes.c_float)
+I64P = ctypes.POINTER(ctypes.c_int64)
+U64P = ctypes.POINTER(ctypes.c_ulonglong)
+
+
+def P(a):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(FP)
+
+
+_cache = {}
+
+
+def oracle():
+    if "orc" not in _cache:
+        lib = ctypes.CDLL(os.path.join(REPO, "oracle", "librbox_oracle.so"))
+        lib.orc_ref_iou.restype = ctypes.c_float
+        lib.orc_ref_iou_fma.restype = ctypes.c_float
+        lib.orc_skew_iou.restype = ctypes.c_double
+        _cache["orc"] = lib
+    return _cache["orc"]
+
+
+def ref_lib(kind):
+    """kind in {'host', 'host_fma', 'cuda'}; returns None when oracle/_ref was never built."""
+    key = "ref_" + kind
+    if key not in _cache:
+        path = os.path.join(REPO, "oracle", "_ref", "libref_rnms_%s.so" % kind)
+        if os.path.exists(path):
+            lib = ctypes.CDLL(path)
+            if kind.startswith("host"):
+                lib.ref_host_iou.restype = ctypes.c_float
+            _cache[key] = lib
+        else:
+            _cache[key] = None
+    return _cache[key]
+
+
+def gen_boxes(n, seed, canvas=608.0):
+    """config-2 generator: cx,cy~U[0,canvas), area~U[792,15803), ratio~U[4,9), theta~U(-pi/2,pi/2)."""
+    g = torch.Generator().manual_seed(seed)
+    cx = torch.rand(n, generator=g) * canvas
+    cy = torch.rand(n, generator=g) * canvas
+    area = 792 + torch.rand(n, generator=g) * (15803 - 792)
+    ratio = 4 + torch.rand(n, generator=g) * 5
+    w = (area * ratio).sqrt()
+    h = (area / ratio).sqrt()
+    th = (torch.rand(n, generator=g) - 0.5) * math.pi
+    return torch.stack([cx, cy, w, h, th], 1).float()
+
+
+def tie_free_scores(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.linspace(0.01, 1, n)[torch.randperm(n, generator=g)].float()
+
+
+def gen_dets(n, seed, canvas=608.0):
+    return torch.cat([gen_boxes(n, seed, canvas), tie_free_scores(n, seed + 1000)[:, None]], 1).contiguous()
+
+
+def orc_rnms(dets_np, thr, variant=0):
+    d = np.ascontiguousarray(dets_np, dtype=np.float32)
+    keep = np.empty(len(d), np.int64)
+    k = oracle().orc_rnms(P(d), len(d), ctypes.c_float(thr), keep.ctypes.data_as(I64P), variant)
+    return keep[:k].copy()
+
+
+def orc_skew_pairwise(a_np, b_np, mode=0):
+    a = np.ascontiguousarray(a_np, dtype=np.float32)
+    b = np.ascontiguousarray(b_np, dtype=np.float32)
+    out = np.empty((len(a), len(b)), np.float32)
+    oracle().orc_skew_iou_pairwise(P(a), len(a), a.shape[1], P(b), len(b), b.shape[1], mode, P(out))
+    return out
+
+
+def orc_skew_paired(a_np, b_np, mode=0):
+    a = np.ascontiguousarray(a_np, dtype=np.float32)
+    b = np.ascontiguousarray(b_np, dtype=np.float32)
+    out = np.empty(len(a), np.float32)
+    oracle().orc_skew_iou_paired(P(a), P(b), len(a), a.shape[1], b.shape[1], mode, P(out))
+    return out
+
+
+def adversarial_dets(seed=7):
+    """Degenerate NMS inputs: exact duplicates, collinear same-angle neighbours, shared edges, concentric boxes,
+    zero-area boxes, NaN box; tie-free scores."""
+    base = gen_boxes(96, seed, 120.0)
+    rows = [base]
+    rows.append(base[:32].clone())                                   # exact duplicates
+    sh = base[32:64].clone(); sh[:, 0] += sh[:, 2] * torch.cos(sh[:, 4]); sh[:, 1] += sh[:, 2] * torch.sin(sh[:, 4])
+    rows.append(sh)                                                  # shifted by w along own axis: shared short edge
+    aa = base[:16].clone(); aa[:, 4] = 0.0; rows.append(aa)           # axis aligned
+    ab = aa.clone(); ab[:, 0] += ab[:, 2]; rows.append(ab)            # touching axis-aligned neighbours
+    cc = base[64:80].clone(); cc[:, 2:4] *= 0.5; rows.append(cc)      # concentric smaller
+    z = base[80:88].clone(); z[:, 2] = 0.0; rows.append(z)            # zero width
+    nn_ = base[88:90].clone(); nn_[:, 0] = float("nan"); rows.append(nn_)
+    b = torch.cat(rows, 0)
+    return torch.cat([b, tie_free_scores(len(b), seed + 1)[:, None]], 1).contiguous()
