@@ -157,11 +157,11 @@ def main():
         if rank != 0:
             return
         if args.workload == "riou":
-            cb, times = cpu_riou(sample_rows=16 * cpu_threads(), steps=max(1, min(K, 3)) + min(W, 1))
-            workload = "rotated IoU 10k x 10k (config 2), bounded sample per step"
+            cb, times = cpu_riou(sample_rows=10000, steps=max(1, min(K, 3)) + min(W, 1))
+            workload = "rotated IoU 10k x 10k (config 2), the full 1e8 pairs per step"
         elif args.workload == "rnms":
-            cb, times = cpu_rnms(4000, steps=max(1, min(K, 3)))
-            workload = "rotated NMS (config 3), bounded sample of 4000 boxes per step"
+            cb, times = cpu_rnms(20000, steps=max(1, min(K, 2)))
+            workload = "rotated NMS (config 3), the full 20000 boxes per step"
         else:
             print(json.dumps({"impl": "reference", "unavailable": "detect workload has no CPU reference arm yet"}))
             return
@@ -320,9 +320,9 @@ def main():
            "gpu_launches": int(launches), "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
         if args.workload == "riou":
-            out["cpu_baseline"], _ = cpu_riou(sample_rows=16 * cpu_threads())
+            out["cpu_baseline"], _ = cpu_riou(sample_rows=10000, steps=2)
         else:
-            out["cpu_baseline"], _ = cpu_rnms(4000)
+            out["cpu_baseline"], _ = cpu_rnms(20000)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
