@@ -117,6 +117,8 @@ static int in_rect_(float x, float y, const float* pts) {
   return abab >= abap && abap >= 0 && adad >= adap && adap >= 0;
 }
 
+int SUFFIX(orc_last_npts) = 0; /* candidate count of the last inter_pts_ call, BEFORE the clamp (diagnostics) */
+
 /* :162-194 ; the reference buffer holds 8 points and is not bounds-checked -- we stop storing at 8 */
 static int inter_pts_(const float* p1, const float* p2, float* out) {
   int n = 0;
@@ -137,6 +139,7 @@ static int inter_pts_(const float* p1, const float* p2, float* out) {
         if (n < 8) { out[2 * n] = tmp[0]; out[2 * n + 1] = tmp[1]; }
         n++;
       }
+  SUFFIX(orc_last_npts) = n;
   return n > 8 ? 8 : n;
 }
 
