@@ -123,6 +123,58 @@ int ryolo_yolo_decode(const float* p, int bs, int na, int nc, int ny, int nx, co
                       float stride, float context_factor, int arc_default, float* io_out,
                       int io_rows_total, int row_offset, float* p_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------ *
+ * Conv2d -> folded BatchNorm -> PReLU (+ residual, + x2 upsample) blocks
+ * (reference: create_modules, model/models.py:49-66; shortcut add :281-282; nn.Upsample :93-94;
+ *  BN folding utils/torch_utils.py:45-69).  sm_100a tcgen05 implicit GEMM, bf16 in / fp32 accumulate.
+ *
+ * Activations live in HBM as "padded NHWC": [B, H+2, W+2, Cs] bf16 with a one-pixel ZERO halo
+ * (zeroed once by the owner of the buffer; these kernels never write it), channels contiguous
+ * with channel stride Cs >= C, so that a 3x3/stride-1 conv is nine row-shifted GEMMs over the
+ * flat pixel index and needs no im2col buffer, and channel concatenation (route layers,
+ * models.py:269-278) is a write at a channel offset into a wider buffer.  Channel counts are
+ * padded to multiples of 64 with zeros (the K chunk of the GEMM).
+ * ------------------------------------------------------------------------------------------ */
+#define RYOLO_DT_BF16 0
+#define RYOLO_DT_F32 1
+
+typedef struct ryolo_conv_desc {
+  int32_t batch;       /* B                                                                   */
+  int32_t in_h, in_w;  /* input spatial size (unpadded)                                       */
+  int32_t cin;         /* channels read by this conv                                          */
+  int32_t cin_stride;  /* channel stride of the input buffer (>= round_up(cin, 64))           */
+  int32_t cout;        /* filters                                                             */
+  int32_t cout_stride; /* channel stride of the bf16 output buffer (>= padded cout)           */
+  int32_t ksize;       /* 1 or 3 (pad = (k-1)/2 as in models.py:53)                           */
+  int32_t stride;      /* 1 or 2                                                              */
+  int32_t has_act;     /* 1: PReLU with scalar `slope` (cfg activation=leaky), 0: linear      */
+  float slope;         /* PReLU weight (nn.PReLU(num_parameters=1), models.py:65)             */
+  int32_t has_residual;/* 1: add `residual` after the activation (shortcut, models.py:281-282) */
+  int32_t res_stride;  /* channel stride of the residual buffer (padded NHWC at OUTPUT size)  */
+  int32_t upsample2x;  /* 1: replicate each output pixel into the 2x2 block of a 2H x 2W output
+                          buffer (nearest x2 folded into the producer)                        */
+  int32_t out_dtype;   /* RYOLO_DT_BF16: padded NHWC; RYOLO_DT_F32: plain NCHW [B,cout,H,W]
+                          (the three linear heads feeding ryolo_yolo_decode)                  */
+} ryolo_conv_desc;
+
+/* Pack reference-layout weights [cout, cin, k, k] fp32 (nn.Conv2d.weight), times an optional
+ * per-filter scale (folded BN: gamma / sqrt(var + eps)), into the bf16 GEMM operand
+ * [k*k][cout_pad][cin_pad] (zero padded).  Device pointers. */
+size_t ryolo_conv_packed_weight_bytes(const ryolo_conv_desc* d);
+int ryolo_conv_pack_weights(const ryolo_conv_desc* d, const float* weight, const float* scale,
+                            void* packed_out, void* stream);
+/* y = act(conv(x, W') + bias) [+ residual].  bias: fp32 [cout_pad] (zero beyond cout). */
+size_t ryolo_conv_workspace_bytes(const ryolo_conv_desc* d);
+int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, const void* packed_w,
+                          const float* bias, const void* residual, void* y, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* First layer (cin = 3, 3x3, stride 1): fp32 NCHW image [B,3,H,W] -> bf16 padded NHWC with
+ * channel stride cout_stride (channels >= cout zero-filled).  weight [cout,3,3,3] fp32 with BN
+ * folded, bias [cout].  Direct CUDA-core kernel: K = 27 is too thin for the tensor pipe. */
+int ryolo_conv_first_fwd(const float* img, int batch, int h, int w, const float* weight,
+                         const float* bias, int cout, float slope, void* y, int cout_stride,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,7 @@ class ConvDesc(ctypes.Structure):
                 ("cin", ctypes.c_int32), ("cin_stride", ctypes.c_int32), ("cout", ctypes.c_int32),
                 ("cout_stride", ctypes.c_int32), ("ksize", ctypes.c_int32), ("stride", ctypes.c_int32),
                 ("has_act", ctypes.c_int32), ("slope", ctypes.c_float), ("has_residual", ctypes.c_int32),
-                ("upsample2x", ctypes.c_int32), ("out_dtype", ctypes.c_int32)]
+                ("res_stride", ctypes.c_int32), ("upsample2x", ctypes.c_int32), ("out_dtype", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/ryolo.h declares (tests/test_abi.py checks it)
@@ -47,6 +47,11 @@ SIGNATURES = {
     "ryolo_nms_filter_workspace_bytes": (_sz, [_i]),
     "ryolo_nms_filter": (_i, [_vp, _i, _i, _f, _f, _vp, _i, _vp, _vp, _sz, _vp]),
     "ryolo_yolo_decode": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _f, _f, _i, _vp, _i, _i, _vp, _vp]),
+    "ryolo_conv_packed_weight_bytes": (_sz, [ctypes.POINTER(ConvDesc)]),
+    "ryolo_conv_pack_weights": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "ryolo_conv_workspace_bytes": (_sz, [ctypes.POINTER(ConvDesc)]),
+    "ryolo_conv_bn_act_fwd": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ryolo_conv_first_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _f, _vp, _i, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)

@@ -1,0 +1,568 @@
+// Conv2d -> (folded) BatchNorm -> PReLU [-> + residual] as an sm_100a implicit GEMM.
+//
+// Replaces the nn.Sequential(Conv2d, BatchNorm2d, PReLU) blocks the reference builds in create_modules
+// (model/models.py:49-66) plus the shortcut add (models.py:281-282) and the nearest x2 upsample (models.py:93-94)
+// that follow some of them; BN is folded as in utils/torch_utils.py:45-69 (scale into the weights at pack time,
+// shift into the epilogue bias).
+//
+// Layout.  Activations are bf16 "padded NHWC": [B][H+2][W+2][Cs] with a one-pixel ZERO halo (zeroed once at
+// allocation, never written afterwards).  With the halo in memory, a 3x3 / stride-1 / pad-1 convolution is nine
+// GEMMs that differ only by a constant shift of the FLAT pixel index  p = (b*(H+2) + y)*(W+2) + x :
+//        out[p, :] = sum_{tap=(dy,dx)}  A[p + dy*(W+2) + dx, :] * W_tap            (valid for every interior p)
+// so the A operand of tap t is a plain 2-D TMA box [128 pixels x 64 channels] whose row coordinate is shifted by
+// the tap offset; rows that fall outside [0, NP) are zero-filled by TMA.  No im2col buffer, no gather.  The GEMM
+// also produces values at halo positions; the epilogue simply does not store them.  Cost of that: (H+2)(W+2)/HW
+// extra MMA rows (5 % at 76^2, 11 % at 38^2, 22 % at 19^2).
+// Stride-2 layers (5 of 75) run the same stride-1 GEMM on the input grid and store only the even pixels
+// (v1: 4x MMA waste on 12 % of the FLOPs; a strided 3-D TMA box is the planned replacement).
+//
+// Kernel.  Persistent, warp-specialised, one CTA per SM, tile = 128 pixels x BN filters, BK = 64 channels:
+//   warp 0   TMA producer: per k-step one A box (shifted by the tap offset) + one B box into a 128B-swizzled
+//            shared-memory stage, completion on an mbarrier (expect_tx);
+//   warp 1   MMA issuer: one elected thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
+//            per stage, accumulating in TMEM; tcgen05.commit releases the stage / publishes the accumulator;
+//   warp 2   TMEM allocator (2 accumulator stages x BN fp32 columns);
+//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time -> +bias -> PReLU -> +residual -> bf16 -> 64-byte
+//            contiguous stores per pixel (or fp32 NCHW for the three linear heads), overlapped with the next
+//            tile's MMAs through the second accumulator stage.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ryolo {
+
+constexpr int BM = 128;  // pixels per tile (UMMA M, TMEM lanes)
+constexpr int BK = 64;   // channels per k-step = one 128-byte swizzle row of bf16
+constexpr int CONV_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups of 1024 B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) /*LBO (unused for swizzled K-major)*/ |
+         ((uint64_t)(1024 >> 4) << 32) /*SBO*/ | (1ull << 46) /*descriptor version (Blackwell)*/ |
+         (2ull << 61) /*SWIZZLE_128B*/;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct ConvParams {
+  int np;             // B * (H+2) * (W+2): GEMM M
+  int hp, wp;         // padded input height / width
+  int taps;           // 1 or 9
+  int kchunks;        // cin_pad / 64
+  int cout;           // real filters
+  int cout_pad;       // rows per tap in the packed weight
+  int n_tiles;        // cout_pad / BN
+  int m_tiles;
+  int stride;         // 1 or 2
+  int oh, ow;         // output spatial size (unpadded)
+  int out_cs;         // channel stride of the output buffer
+  int res_cs;         // channel stride of the residual buffer
+  int has_act, has_res, upsample2x, out_f32_nchw;
+  float slope;
+  const float* bias;               // [cout_pad]
+  const __nv_bfloat16* residual;   // padded NHWC like the output, or null
+  void* out;
+};
+
+template <int BN>
+struct ConvSmem {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTileBytes = kStages * kStageBytes;
+  static constexpr int kBarOffset = kTileBytes;                       // full[kStages], empty[kStages], tfull[2], tempty[2]
+  static constexpr int kBiasOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;
+  static constexpr int kTotal = kBiasOffset + BN * 4 + 1024 /*alignment slack*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvParams p) {
+  using S = ConvSmem<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + S::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S::kStages + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOffset + (2 * S::kStages + 4) * 8);
+  float* s_bias = reinterpret_cast<float*>(smem_gen + S::kBiasOffset);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.taps * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::kStages; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        const int p0 = mt * BM;
+        for (int kk = 0; kk < k_iters; kk++) {
+          const int tap = kk / p.kchunks, kc = kk % p.kchunks;
+          int off = 0;
+          if (p.taps == 9) off = (tap / 3 - 1) * p.wp + (tap % 3 - 1);
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * S::kStageBytes;
+          mbar_expect_tx(full_bar(stage), S::kStageBytes);
+          tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, p0 + off);
+          tma_load_2d(sa + S::kABytes, &map_b, full_bar(stage), kc * BK, tap * p.cout_pad + nt * BN);
+          if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kk = 0; kk < k_iters; kk++) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * S::kStageBytes;
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++) {
+            // +32 bytes (16 bf16) along K inside the swizzle atom: start-address field += 2
+            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kk | k) != 0);
+          }
+          tc_commit(empty_bar(stage));  // frees the stage when these MMAs have read it
+          if (kk == k_iters - 1) tc_commit(tfull_bar(acc));
+          if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      // bias for this n-tile -> smem (epilogue warps only: named barrier 1, 128 threads)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 128; i < BN; i += 128) s_bias[i] = p.bias[nt * BN + i];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      const int pix = mt * BM + q * 32 + lane;  // flat padded input-grid pixel of this thread's row
+      bool valid = pix < p.np;
+      int b = 0, yp = 0, xp = 0;
+      if (valid) {
+        xp = pix % p.wp;
+        const int t = pix / p.wp;
+        yp = t % p.hp;
+        b = t / p.hp;
+        valid = xp >= 1 && xp <= p.wp - 2 && yp >= 1 && yp <= p.hp - 2;
+      }
+      int oy = yp - 1, ox = xp - 1;
+      if (p.stride == 2) {
+        valid = valid && ((oy & 1) == 0) && ((ox & 1) == 0);
+        oy >>= 1;
+        ox >>= 1;
+      }
+      valid = valid && oy < p.oh && ox < p.ow;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+
+      const int n_valid = min(BN, p.cout - nt * BN);  // real filters in this n-tile (may be <= 0 for pure padding)
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(t_row + c0, v);
+        tc_wait_ld();
+        if (!valid) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float x = __uint_as_float(v[j]) + s_bias[c0 + j];
+          if (p.has_act) x = x > 0.f ? x : p.slope * x;
+          f[j] = x;
+        }
+        if (p.out_f32_nchw) {
+          // heads: fp32 [B, cout, oh, ow]
+          float* o = reinterpret_cast<float*>(p.out);
+          const size_t plane = (size_t)p.oh * p.ow;
+          const size_t base = ((size_t)b * p.cout) * plane + (size_t)oy * p.ow + ox;
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (c0 + j < n_valid) o[base + (size_t)(nt * BN + c0 + j) * plane] = f[j];
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+          const int ohp = (p.upsample2x ? 2 * p.oh : p.oh) + 2, owp = (p.upsample2x ? 2 * p.ow : p.ow) + 2;
+          if (p.has_res) {
+            const __nv_bfloat16* r =
+                p.residual + (((size_t)b * (p.oh + 2) + oy + 1) * (p.ow + 2) + ox + 1) * p.res_cs + nt * BN + c0;
+            const uint4* r4 = reinterpret_cast<const uint4*>(r);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              const uint4 rv = __ldg(r4 + g);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const float2 ff = __bfloat1622float2(h[e]);
+                f[g * 8 + e * 2] += ff.x;
+                f[g * 8 + e * 2 + 1] += ff.y;
+              }
+            }
+          }
+          uint4 pk[4];
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(f[g * 8 + e * 2], f[g * 8 + e * 2 + 1]);
+            pk[g] = *reinterpret_cast<uint4*>(h);
+          }
+          const int reps = p.upsample2x ? 2 : 1;
+          for (int ry = 0; ry < reps; ry++)
+            for (int rx = 0; rx < reps; rx++) {
+              const int yy = (p.upsample2x ? 2 * oy + ry : oy) + 1, xx = (p.upsample2x ? 2 * ox + rx : ox) + 1;
+              uint4* o4 = reinterpret_cast<uint4*>(o + (((size_t)b * ohp + yy) * owp + xx) * p.out_cs + nt * BN + c0);
+#pragma unroll
+              for (int g = 0; g < 4; g++) o4[g] = pk[g];
+            }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing: [cout, cin, k, k] fp32 (* per-filter scale) -> bf16 [k*k][cout_pad][cin_pad], zero padded
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void conv_pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ scale, int cout, int cin,
+                                         int ks, int cout_pad, int cin_pad, __nv_bfloat16* __restrict__ out) {
+  const size_t total = (size_t)ks * ks * cout_pad * cin_pad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad);
+    const int co = (int)((i / cin_pad) % cout_pad);
+    const int tap = (int)(i / ((size_t)cin_pad * cout_pad));
+    float v = 0.f;
+    if (ci < cin && co < cout) {
+      v = w[(((size_t)co * cin + ci) * ks + tap / ks) * ks + tap % ks];
+      if (scale) v *= scale[co];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// first layer: fp32 NCHW image, cin = 3, 3x3 / stride 1 / pad 1 -> bf16 padded NHWC (cout real + zero pad channels)
+// ---------------------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ img, int batch, int h, int w,
+                                                         const float* __restrict__ weight, const float* __restrict__ bias,
+                                                         float slope, __nv_bfloat16* __restrict__ out, int out_cs) {
+  __shared__ float s_w[COUT * 27];
+  __shared__ float s_b[COUT];
+  for (int i = threadIdx.x; i < COUT * 27; i += blockDim.x) s_w[i] = weight[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_b[i] = bias[i];
+  __syncthreads();
+  const size_t npix = (size_t)batch * h * w;
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int x = (int)(pix % w);
+  const int y = (int)((pix / w) % h);
+  const int b = (int)(pix / ((size_t)w * h));
+  float in[27];
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++) {
+        const int yy = y + dy - 1, xx = x + dx - 1;
+        in[c * 9 + dy * 3 + dx] =
+            (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(img + (((size_t)b * 3 + c) * h + yy) * w + xx) : 0.f;
+      }
+  __nv_bfloat16* o = out + (((size_t)b * (h + 2) + y + 1) * (w + 2) + x + 1) * out_cs;
+#pragma unroll 1
+  for (int co = 0; co < COUT; co += 8) {
+    __nv_bfloat162 hv[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      float a0 = s_b[co + 2 * e], a1 = s_b[co + 2 * e + 1];
+#pragma unroll
+      for (int k = 0; k < 27; k++) {
+        a0 = fmaf(in[k], s_w[(co + 2 * e) * 27 + k], a0);
+        a1 = fmaf(in[k], s_w[(co + 2 * e + 1) * 27 + k], a1);
+      }
+      a0 = a0 > 0.f ? a0 : slope * a0;
+      a1 = a1 > 0.f ? a1 : slope * a1;
+      hv[e] = __floats2bfloat162_rn(a0, a1);
+    }
+    *reinterpret_cast<uint4*>(o + co) = *reinterpret_cast<uint4*>(hv);
+  }
+  // zero the padding channels [COUT, out_cs) so that the next layer's 64-wide K chunk reads zeros
+  for (int co = COUT; co < out_cs; co += 8) *reinterpret_cast<uint4*>(o + co) = make_uint4(0, 0, 0, 0);
+}
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct ConvGeom {
+  int cin_pad, cout_pad, bn, taps;
+};
+static ConvGeom conv_geom(const ryolo_conv_desc* d) {
+  ConvGeom g;
+  g.cin_pad = round_up(d->cin, 64);
+  g.bn = d->cout > 128 ? 256 : (d->cout > 64 ? 128 : 64);
+  g.cout_pad = round_up(d->cout, g.bn);
+  g.taps = d->ksize * d->ksize;
+  return g;
+}
+
+static int encode_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                         uint32_t box_inner, uint32_t box_rows) {
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    const char* s = nullptr;
+    cuGetErrorString(r, &s);
+    set_err("cuTensorMapEncodeTiled failed: %s (inner=%llu rows=%llu stride=%llu box=%ux%u base=%p)", s ? s : "?",
+            (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_inner, box_rows,
+            base);
+    return RYOLO_E_CUDA;
+  }
+  return RYOLO_OK;
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t stream) {
+  using S = ConvSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RYOLO_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    RYOLO_CUDA_TRY(cudaGetDevice(&dev));
+    RYOLO_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  conv_igemm_kernel<BN><<<grid, CONV_THREADS, S::kTotal, stream>>>(ma, mb, p);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+}  // namespace ryolo
+
+using namespace ryolo;
+
+extern "C" size_t ryolo_conv_packed_weight_bytes(const ryolo_conv_desc* d) {
+  if (!d) return 0;
+  const ConvGeom g = conv_geom(d);
+  return (size_t)g.taps * g.cout_pad * g.cin_pad * 2;
+}
+
+extern "C" int ryolo_conv_pack_weights(const ryolo_conv_desc* d, const float* weight, const float* scale, void* packed_out,
+                                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(d && weight && packed_out);
+  RYOLO_ARG_CHECK(d->ksize == 1 || d->ksize == 3);
+  const ConvGeom g = conv_geom(d);
+  const size_t total = (size_t)g.taps * g.cout_pad * g.cin_pad;
+  const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+  conv_pack_weights_kernel<<<blocks, 256, 0, stream>>>(weight, scale, d->cout, d->cin, d->ksize, g.cout_pad, g.cin_pad,
+                                                        static_cast<__nv_bfloat16*>(packed_out));
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" size_t ryolo_conv_workspace_bytes(const ryolo_conv_desc* d) {
+  (void)d;
+  return 0;  // the implicit GEMM needs no scratch (no im2col buffer)
+}
+
+extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, const void* packed_w, const float* bias,
+                                     const void* residual, void* y, void* workspace, size_t workspace_bytes,
+                                     void* stream_) {
+  (void)workspace;
+  (void)workspace_bytes;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(d && x && packed_w && bias && y);
+  RYOLO_ARG_CHECK(d->batch > 0 && d->in_h > 0 && d->in_w > 0 && d->cin > 0 && d->cout > 0);
+  RYOLO_ARG_CHECK(d->ksize == 1 || d->ksize == 3);
+  RYOLO_ARG_CHECK(d->stride == 1 || d->stride == 2);
+  RYOLO_ARG_CHECK(!(d->stride == 2 && d->upsample2x));
+  RYOLO_ARG_CHECK(!d->has_residual || (residual != nullptr && d->stride == 1 && !d->upsample2x &&
+                                        d->res_stride % 8 == 0 && d->out_dtype == RYOLO_DT_BF16));
+  const ConvGeom g = conv_geom(d);
+  RYOLO_ARG_CHECK(d->cin_stride >= g.cin_pad && d->cin_stride % 8 == 0);  // 64-wide K chunks read the channel padding
+  RYOLO_ARG_CHECK(d->out_dtype == RYOLO_DT_BF16 || d->out_dtype == RYOLO_DT_F32);
+  if (d->out_dtype == RYOLO_DT_BF16) RYOLO_ARG_CHECK(d->cout_stride >= g.cout_pad && d->cout_stride % 8 == 0);
+  RYOLO_ARG_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+
+  ConvParams p;
+  p.hp = d->in_h + 2;
+  p.wp = d->in_w + 2;
+  const long long np = (long long)d->batch * p.hp * p.wp;
+  RYOLO_ARG_CHECK(np < (1ll << 31) - 4096);
+  p.np = (int)np;
+  p.taps = g.taps;
+  p.kchunks = g.cin_pad / 64;
+  p.cout = d->cout;
+  p.cout_pad = g.cout_pad;
+  p.n_tiles = g.cout_pad / g.bn;
+  p.m_tiles = (p.np + BM - 1) / BM;
+  p.stride = d->stride;
+  p.oh = d->stride == 2 ? (d->in_h + 1) / 2 : d->in_h;   // k=3,pad=1 (or k=1,pad=0) with stride 2: ceil(h/2)
+  p.ow = d->stride == 2 ? (d->in_w + 1) / 2 : d->in_w;
+  p.out_cs = d->cout_stride;
+  p.res_cs = d->res_stride;
+  p.has_act = d->has_act;
+  p.has_res = d->has_residual;
+  p.upsample2x = d->upsample2x;
+  p.out_f32_nchw = d->out_dtype == RYOLO_DT_F32;
+  p.slope = d->slope;
+  p.bias = bias;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.out = y;
+
+  CUtensorMap ma, mb;
+  int st = encode_map_2d(&ma, x, (uint64_t)g.cin_pad, (uint64_t)p.np, (uint64_t)d->cin_stride * 2, BK, BM);
+  if (st != RYOLO_OK) return st;
+  st = encode_map_2d(&mb, packed_w, (uint64_t)g.cin_pad, (uint64_t)g.taps * g.cout_pad, (uint64_t)g.cin_pad * 2, BK,
+                     (uint32_t)g.bn);
+  if (st != RYOLO_OK) return st;
+  if (g.bn == 256) return launch_conv<256>(ma, mb, p, stream);
+  if (g.bn == 128) return launch_conv<128>(ma, mb, p, stream);
+  return launch_conv<64>(ma, mb, p, stream);
+}
+
+extern "C" int ryolo_conv_first_fwd(const float* img, int batch, int h, int w, const float* weight, const float* bias,
+                                    int cout, float slope, void* y, int cout_stride, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(img && weight && bias && y && batch > 0 && h > 0 && w > 0);
+  RYOLO_ARG_CHECK(cout == 32 || cout == 16);
+  RYOLO_ARG_CHECK(cout_stride >= cout && cout_stride % 8 == 0);
+  const size_t npix = (size_t)batch * h * w;
+  const unsigned blocks = (unsigned)((npix + 255) / 256);
+  if (cout == 32)
+    conv_first_kernel<32><<<blocks, 256, 0, stream>>>(img, batch, h, w, weight, bias, slope,
+                                                      static_cast<__nv_bfloat16*>(y), cout_stride);
+  else
+    conv_first_kernel<16><<<blocks, 256, 0, stream>>>(img, batch, h, w, weight, bias, slope,
+                                                      static_cast<__nv_bfloat16*>(y), cout_stride);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}

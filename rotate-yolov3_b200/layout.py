@@ -1,0 +1,62 @@
+"""Padded-NHWC bf16 activation layout helpers (see include/ryolo.h, conv section) and the thin Python binding of
+the conv entry points.  Pure tensor plumbing: allocation and layout conversion for tests / model I/O."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def alloc_padded(batch, h, w, cs, device):
+    """[B, H+2, W+2, Cs] bf16, zero everywhere (the halo must stay zero; kernels never write it)."""
+    return torch.zeros((batch, h + 2, w + 2, cs), dtype=torch.bfloat16, device=device)
+
+
+def to_padded_nhwc(x_nchw, cs=None):
+    b, c, h, w = x_nchw.shape
+    cs = cs or round_up(c, 64)
+    buf = alloc_padded(b, h, w, cs, x_nchw.device)
+    buf[:, 1:h + 1, 1:w + 1, :c] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return buf
+
+
+def from_padded_nhwc(buf, c, ch_offset=0):
+    h, w = buf.shape[1] - 2, buf.shape[2] - 2
+    return buf[:, 1:h + 1, 1:w + 1, ch_offset:ch_offset + c].permute(0, 3, 1, 2).float().contiguous()
+
+
+def make_desc(batch, in_h, in_w, cin, cin_stride, cout, cout_stride, ksize, stride=1, has_act=True, slope=0.1,
+              has_residual=False, res_stride=0, upsample2x=False, out_f32=False):
+    return _lib.ConvDesc(batch, in_h, in_w, cin, cin_stride, cout, cout_stride, ksize, stride, int(has_act),
+                         float(slope), int(has_residual), res_stride, int(upsample2x),
+                         _lib.DT_F32 if out_f32 else _lib.DT_BF16)
+
+
+def pack_weights(desc, weight, scale=None):
+    """weight [cout, cin, k, k] fp32 CUDA (+ optional per-filter scale) -> packed bf16 GEMM operand (uint8 tensor)."""
+    nbytes = _lib.lib.ryolo_conv_packed_weight_bytes(ctypes.byref(desc))
+    out = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    w = weight.detach().float().contiguous()
+    s = scale.detach().float().contiguous() if scale is not None else None
+    st = _lib.lib.ryolo_conv_pack_weights(ctypes.byref(desc), _lib.ptr(w), _lib.ptr(s) if s is not None else None,
+                                          _lib.ptr(out), _lib.stream_ptr(weight.device))
+    _lib.check(st, "ryolo_conv_pack_weights")
+    return out
+
+
+def padded_bias(desc, bias):
+    cout_pad = _lib.lib.ryolo_conv_packed_weight_bytes(ctypes.byref(desc)) // (2 * desc.ksize * desc.ksize * round_up(desc.cin, 64))
+    b = torch.zeros(cout_pad, dtype=torch.float32, device=bias.device)
+    b[:desc.cout] = bias.detach().float()
+    return b
+
+
+def conv_fwd(desc, x_ptr, packed_w, bias, y_ptr, residual_ptr=None, device=None):
+    st = _lib.lib.ryolo_conv_bn_act_fwd(ctypes.byref(desc), ctypes.c_void_p(x_ptr), _lib.ptr(packed_w), _lib.ptr(bias),
+                                        ctypes.c_void_p(residual_ptr) if residual_ptr else None,
+                                        ctypes.c_void_p(y_ptr), None, 0, _lib.stream_ptr(device))
+    _lib.check(st, "ryolo_conv_bn_act_fwd")

@@ -1,0 +1,114 @@
+"""tcgen05 implicit-GEMM conv blocks vs a plain PyTorch fp32 reference of the same op (conv2d + bias + PReLU
+[+ residual] [+ nearest x2]).  Inputs/weights are rounded to bf16 first (the kernel's operand type), so the only
+differences are fp32 accumulation order (fp32-NCHW outputs: 1e-4 relative to the layer's output scale, the
+north_star tolerance) and the final bf16 rounding (bf16 outputs: 1 bf16 ulp = 2^-8 relative)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, b, stride, slope, act, res=None, up=False):
+    k = w.shape[-1]
+    y = F.conv2d(x, w, b, stride=stride, padding=(k - 1) // 2)
+    if act:
+        y = torch.where(y > 0, y, slope * y)
+    if res is not None:
+        y = y + res
+    if up:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    return y
+
+
+def _run(batch, h, w, cin, cout, k, stride=1, act=True, residual=False, up=False, f32=False, seed=0, cin_extra=0,
+         cout_extra=0):
+    from rotate_yolov3_b200 import layout as L
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(batch, cin, h, w, generator=g).to(dev).to(torch.bfloat16).float()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev).to(torch.bfloat16).float()
+    bias = torch.randn(cout, generator=g).to(dev)
+    slope = 0.1
+    oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
+    cin_cs = L.round_up(cin, 64) + cin_extra
+    xb = L.to_padded_nhwc(x, cin_cs)
+    if cin_extra:
+        xb[..., L.round_up(cin, 64):] = 7.0      # neighbouring channels of a concat buffer must not leak in
+    desc = L.make_desc(batch, h, w, cin, cin_cs, cout, 0, k, stride, act, slope, residual, 0, up, f32)
+    bn = 256 if cout > 128 else (128 if cout > 64 else 64)
+    cout_pad = L.round_up(cout, bn)
+    cout_cs = cout_pad + cout_extra
+    desc.cout_stride = cout_cs
+    res_t, res_buf = None, None
+    if residual:
+        res_t = torch.randn(batch, cout, oh, ow, generator=g).to(dev).to(torch.bfloat16).float()
+        res_buf = L.to_padded_nhwc(res_t, cout_pad + 64)
+        desc.res_stride = cout_pad + 64
+    pw = L.pack_weights(desc, wt)
+    pb = L.padded_bias(desc, bias)
+    assert pb.numel() == cout_pad
+    if f32:
+        y = torch.full((batch, cout, oh, ow), float("nan"), device=dev)
+    else:
+        y = L.alloc_padded(batch, oh * (2 if up else 1), ow * (2 if up else 1), cout_cs, dev)
+        if cout_extra:
+            y[..., cout_pad:] = 3.0
+    L.conv_fwd(desc, xb.data_ptr(), pw, pb, y.data_ptr(), res_buf.data_ptr() if residual else None, dev)
+    torch.cuda.synchronize()
+    want = _ref(x, wt, bias, stride, slope, act, res_t, up)
+    scale = float(want.abs().max())
+    if f32:
+        got = y
+        err = float((got - want).abs().max())
+        assert err <= 1e-4 * scale, (err, scale)
+    else:
+        got = L.from_padded_nhwc(y, cout)
+        err = (got - want).abs()
+        tol = 2.0 ** -8 * want.abs() + 1e-3 * scale * 2.0 ** -8 + 1e-6
+        assert bool((err <= tol).all()), (float(err.max()), scale)
+        # halo untouched (zero), channel padding zero, neighbours of a wider buffer untouched
+        assert float(y[:, 0].abs().max()) == 0 and float(y[:, -1].abs().max()) == 0
+        assert float(y[:, :, 0].abs().max()) == 0 and float(y[:, :, -1].abs().max()) == 0
+        if cout_pad > cout:
+            assert float(y[:, 1:-1, 1:-1, cout:cout_pad].abs().max()) == 0
+        if cout_extra:
+            assert float((y[..., cout_pad:] - 3.0).abs().max()) == 0
+    return err
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(batch=1, h=8, w=8, cin=64, cout=64, k=1),                                  # smallest GEMM, BN=64
+    dict(batch=2, h=19, w=19, cin=64, cout=128, k=3),                               # 9 taps, BN=128
+    dict(batch=2, h=19, w=19, cin=128, cout=256, k=3, residual=True),               # BN=256 + shortcut add
+    dict(batch=3, h=38, w=38, cin=256, cout=128, k=1, up=True, cout_extra=256),     # upsample into a concat buffer
+    dict(batch=2, h=16, w=20, cin=32, cout=64, k=3, stride=2),                      # stride 2, cin padded 32->64
+    dict(batch=2, h=19, w=19, cin=128, cout=504, k=1, act=False, f32=True),         # linear head, fp32 NCHW, 504 = 2 n-tiles
+    dict(batch=1, h=76, w=76, cin=128, cout=256, k=3),                              # many m-tiles (persistent loop)
+    dict(batch=2, h=38, w=38, cin=768, cout=256, k=1, cin_extra=0),                 # long K (12 chunks)
+    dict(batch=2, h=19, w=19, cin=64, cout=32, k=1, cin_extra=128),                 # cout padded 32->64, wide input buffer
+    dict(batch=1, h=19, w=19, cin=512, cout=1024, k=3),                             # 4 n-tiles x 72 k-steps
+])
+def test_conv_block_vs_torch(cfg):
+    _run(**cfg)
+
+
+def test_first_layer_direct_conv():
+    import ctypes
+    import rotate_yolov3_b200 as pkg
+    from rotate_yolov3_b200 import layout as L
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(2, 3, 40, 56, generator=g).to(dev)
+    w = (torch.randn(32, 3, 3, 3, generator=g) / 5).to(dev)
+    b = torch.randn(32, generator=g).to(dev)
+    y = L.alloc_padded(2, 40, 56, 64, dev)
+    y[:, 1:-1, 1:-1, 32:] = 5.0
+    st = pkg._lib.lib.ryolo_conv_first_fwd(pkg._lib.ptr(x), 2, 40, 56, pkg._lib.ptr(w), pkg._lib.ptr(b), 32, 0.1,
+                                           pkg._lib.ptr(y), 64, pkg._lib.stream_ptr(dev))
+    assert st == 0
+    want = _ref(x, w, b, 1, 0.1, True)
+    got = L.from_padded_nhwc(y, 32)
+    assert bool(((got - want).abs() <= 2.0 ** -8 * want.abs() + 1e-5).all())
+    assert float(y[..., 32:].abs().max()) == 0      # channel padding zeroed for the next layer's 64-wide K chunk
+    assert float(y[:, 0].abs().max()) == 0 and float(y[:, :, 0].abs().max()) == 0
