@@ -78,7 +78,7 @@ def build_cuda(verbose=True, force=False):
         with open(stamp, "w") as f:
             f.write(dig)
     if relink:
-        _run([nvcc, "-shared", "-o", LIB] + objs + ["-lcuda"], verbose)
+        _run([nvcc, "-shared", "-o", LIB] + objs, verbose)
     return LIB
 
 
