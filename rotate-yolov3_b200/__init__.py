@@ -7,5 +7,6 @@ importing the package fails loudly when that library has not been built -- there
 from . import _lib  # noqa: F401  (raises ImportError with the build instruction if libryolo.so is missing)
 from .iou import rotated_iou_matrix, skew_bbox_iou  # noqa: F401
 from .nms import nms_filter, non_max_suppression, r_nms  # noqa: F401
+from .models import Darknet, YOLOLayer  # noqa: F401
 
-__all__ = ["r_nms", "non_max_suppression", "nms_filter", "skew_bbox_iou", "rotated_iou_matrix"]
+__all__ = ["r_nms", "non_max_suppression", "nms_filter", "skew_bbox_iou", "rotated_iou_matrix", "Darknet", "YOLOLayer"]

@@ -1,0 +1,357 @@
+"""``Darknet(cfg, hyp, arc).forward`` behind the reference's signature (model/models.py:230-313), executed by
+libryolo.so: every Conv2d -> BatchNorm2d -> PReLU block is one tcgen05 implicit-GEMM launch with BN folded, the
+shortcut add / nearest-x2 upsample / channel concat of the graph fused into the producing conv's epilogue (residual
+read, 2x2 replicated store, store at a channel offset of the shared concat buffer), and the YOLO heads decoded by one
+fused kernel each.
+
+What is kept from the reference so that train.py / test.py / detect.py see the same object:
+  * ``module_defs`` / ``module_list`` / ``routes`` / ``yolo_layers`` / ``hyp`` / ``version`` / ``seen``;
+  * parameter names: ``module_list.{i}.Conv2d.weight``, ``.BatchNorm2d.{weight,bias,running_mean,running_var,
+    num_batches_tracked}``, ``.activation.weight`` (checkpoints and the optimizer split key on them);
+  * YOLO layers expose ``ng, anchor_vec, anchor_wh, stride, nx, ny, na, nc`` (read by model/loss.py:172-174,313);
+  * eval forward returns ``(io [B, sum(na*ny*nx), nc+6], (p0, p1, p2))`` with p_i = [B, na, ny, nx, nc+6].
+
+Scope of this round: the INFERENCE path (eval mode).  Training-mode forward (batch-statistics BN + backward) is the
+next row of SURVEY.md section 8 and raises until it is built -- there is no PyTorch fallback."""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import layout as L
+from .parse_config import parse_model_cfg
+
+
+class YOLOLayer(nn.Module):
+    """reference model/models.py:170-227; decode runs in ryolo_yolo_decode."""
+
+    def __init__(self, anchors, nc, yolo_index, arc, hyp):
+        super().__init__()
+        self.anchors = torch.Tensor(np.asarray(anchors, dtype=np.float64))
+        self.na = len(anchors)
+        self.nc = nc
+        self.nx = 0
+        self.ny = 0
+        self.arc = arc
+        self.hyp = hyp
+        self.yolo_index = yolo_index
+
+    def create_grids(self, img_size, ng, device, dtype=torch.float32):
+        """reference model/model_utils.py:16-35 (without its in-place division bug on CPU: anchors are not
+        modified, anchor_vec is a fresh tensor)."""
+        nx, ny = ng
+        self.img_size = max(img_size)
+        self.stride = self.img_size / max(ng)
+        yv, xv = torch.meshgrid([torch.arange(ny), torch.arange(nx)], indexing="ij")
+        self.grid_xy = torch.stack((xv, yv), 2).to(device).type(dtype).view((1, 1, ny, nx, 2))
+        self.anchor_vec = self.anchors.clone().to(device)
+        self.anchor_vec[:, :2] /= self.stride
+        self.anchor_wh = self.anchor_vec.view(1, self.na, 1, 1, 3).to(device).type(dtype)
+        self.ng = torch.Tensor(ng).to(device)
+        self.nx = nx
+        self.ny = ny
+        self._anchors_dev = self.anchors.to(device=device, dtype=torch.float32).contiguous()
+
+    def decode_into(self, p, img_size, io, rows_total, row_offset):
+        """p: [B, na*(nc+6), ny, nx] fp32 NCHW head output -> writes rows of io, returns the permuted raw view."""
+        bs, ny, nx = p.shape[0], p.shape[-2], p.shape[-1]
+        if (self.nx, self.ny) != (nx, ny) or getattr(self, "_anchors_dev", None) is None or \
+                self._anchors_dev.device != p.device:
+            self.create_grids(img_size, (nx, ny), p.device, p.dtype)
+        pp = torch.empty((bs, self.na, ny, nx, self.nc + 6), dtype=torch.float32, device=p.device)
+        st = _lib.lib.ryolo_yolo_decode(_lib.ptr(p), bs, self.na, self.nc, ny, nx, _lib.ptr(self._anchors_dev),
+                                        float(self.stride), float(self.hyp["context_factor"]),
+                                        1 if "default" in self.arc else 0, _lib.ptr(io), rows_total, row_offset,
+                                        _lib.ptr(pp), _lib.stream_ptr(p.device))
+        _lib.check(st, "ryolo_yolo_decode")
+        return pp
+
+    def forward(self, p, img_size, var=None):
+        if self.training:
+            bs, ny, nx = p.shape[0], p.shape[-2], p.shape[-1]
+            if (self.nx, self.ny) != (nx, ny):
+                self.create_grids(img_size, (nx, ny), p.device, p.dtype)
+            return p.view(bs, self.na, self.nc + 6, self.ny, self.nx).permute(0, 1, 3, 4, 2).contiguous()
+        if "default" not in self.arc:
+            raise NotImplementedError("only the 'default' arcs are decoded by the fused kernel")
+        p = p.float().contiguous()
+        bs, ny, nx = p.shape[0], p.shape[-2], p.shape[-1]
+        rows = self.na * ny * nx
+        io = torch.empty((bs, rows, self.nc + 6), dtype=torch.float32, device=p.device)
+        pp = self.decode_into(p, img_size, io, rows, 0)
+        return io, pp
+
+
+def create_modules(module_defs, arc, hyp):
+    """reference model/models.py:36-164 -- same module structure and names; smart bias init omitted (it always
+    fails in the reference, models.py:132-155)."""
+    hyperparams = module_defs.pop(0)
+    output_filters = [int(hyperparams["channels"])]
+    module_list = nn.ModuleList()
+    routes = []
+    yolo_index = -1
+    filters = output_filters[-1]
+    for i, mdef in enumerate(module_defs):
+        modules = nn.Sequential()
+        t = mdef["type"]
+        if t == "convolutional":
+            bn = int(mdef["batch_normalize"])
+            filters = int(mdef["filters"])
+            k = int(mdef["size"])
+            pad = (k - 1) // 2 if int(mdef["pad"]) else 0
+            modules.add_module("Conv2d", nn.Conv2d(output_filters[-1], filters, k, int(mdef["stride"]), pad, bias=not bn))
+            if bn:
+                modules.add_module("BatchNorm2d", nn.BatchNorm2d(filters, momentum=0.1))
+            if mdef["activation"] == "leaky":
+                modules.add_module("activation", nn.PReLU(num_parameters=1, init=0.10))
+        elif t == "maxpool":
+            k, s = int(mdef["size"]), int(mdef["stride"])
+            mp = nn.MaxPool2d(kernel_size=k, stride=s, padding=int((k - 1) // 2))
+            if k == 2 and s == 1:
+                modules.add_module("ZeroPad2d", nn.ZeroPad2d((0, 1, 0, 1)))
+                modules.add_module("MaxPool2d", mp)
+            else:
+                modules = mp
+        elif t == "upsample":
+            modules = nn.Upsample(scale_factor=int(mdef["stride"]), mode="nearest")
+        elif t == "route":
+            layers = [int(x) for x in mdef["layers"].split(",")]
+            filters = sum(output_filters[l + 1 if l > 0 else l] for l in layers)
+            routes.extend([l if l > 0 else l + i for l in layers])
+        elif t == "shortcut":
+            filters = output_filters[int(mdef["from"])]
+            layer = int(mdef["from"])
+            routes.extend([i + layer if layer < 0 else layer])
+        elif t == "yolo":
+            yolo_index += 1
+            lo, hi = [int(v) for v in mdef["mask"].split("-")]
+            modules = YOLOLayer(anchors=mdef["anchors"][lo:hi + 1], nc=int(mdef["classes"]), hyp=hyp,
+                                yolo_index=yolo_index, arc=arc)
+        else:
+            raise NotImplementedError("layer type %r is outside the hot-path scope (SURVEY.md section 2)" % t)
+        module_list.append(modules)
+        output_filters.append(filters)
+    return module_list, routes
+
+
+class _View:
+    """a [B, H, W, C] activation living in a (possibly wider) padded-NHWC buffer"""
+
+    def __init__(self, buf, ch_off, c, h, w):
+        self.buf, self.ch_off, self.c, self.h, self.w = buf, ch_off, c, h, w
+
+    @property
+    def cs(self):
+        return self.buf.shape[-1]
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + 2 * self.ch_off
+
+
+class Darknet(nn.Module):
+    def __init__(self, cfg, hyp, arc="default"):
+        super().__init__()
+        self.module_defs = parse_model_cfg(cfg)
+        self.net_hyper = self.module_defs[0]
+        self.module_list, self.routes = create_modules(self.module_defs, arc, hyp)
+        self.yolo_layers = [i for i, d in enumerate(self.module_defs) if d["type"] == "yolo"]
+        self.hyp = hyp
+        self.arc = arc
+        self.version = np.array([0, 2, 5], dtype=np.int32)
+        self.seen = np.array([0], dtype=np.int64)
+        self._plan = None
+        self._plan_key = None
+
+    # ------------------------------------------------------------------------------------------------------
+    def fuse(self):
+        """reference models.py:300-313 folds BN into the convs module-by-module; here folding happens when the
+        GEMM operands are packed (every eval forward uses folded weights), so this only drops the cache."""
+        self._plan = None
+
+    def train(self, mode=True):
+        self._plan = None
+        return super().train(mode)
+
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _folded(self, i, device):
+        """(weight [cout,cin,k,k], per-filter scale or None, bias [cout], slope or None) with eval-mode BN folded
+        per utils/torch_utils.py:45-69."""
+        seq = self.module_list[i]
+        conv = seq.Conv2d
+        w = conv.weight.detach().float()
+        if hasattr(seq, "BatchNorm2d"):
+            bn = seq.BatchNorm2d
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            bias = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+            if conv.bias is not None:
+                bias = bias + conv.bias.detach().float() * scale
+        else:
+            scale = None
+            bias = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=device)
+        slope = float(seq.activation.weight.detach().float().item()) if hasattr(seq, "activation") else None
+        return w, scale, bias, slope
+
+    def _build_plan(self, batch, height, width, device):
+        defs = self.module_defs
+        n = len(defs)
+        # ---- static shape walk ----
+        shape = [None] * n   # (C, H, W) of every block's output
+        c, h, w = 3, height, width
+        for i, d in enumerate(defs):
+            t = d["type"]
+            if t == "convolutional":
+                s = int(d["stride"])
+                c, h, w = int(d["filters"]), (h + s - 1) // s, (w + s - 1) // s
+            elif t == "upsample":
+                h, w = h * int(d["stride"]), w * int(d["stride"])
+            elif t == "route":
+                ls = [int(x) for x in d["layers"].split(",")]
+                ls = [l if l > 0 else i + l for l in ls]
+                c = sum(shape[l][0] for l in ls)
+                h, w = shape[ls[0]][1], shape[ls[0]][2]
+            elif t == "shortcut":
+                pass
+            elif t == "yolo":
+                pass
+            else:
+                raise NotImplementedError("block type %r has no sm_100a kernel yet" % t)
+            shape[i] = (c, h, w)
+        # ---- concat groups: route blocks with >1 source write-share one buffer ----
+        target = {}   # materialised layer index -> (buffer, channel offset)
+        views = [None] * n
+        for i, d in enumerate(defs):
+            if d["type"] == "route":
+                ls = [int(x) for x in d["layers"].split(",")]
+                ls = [l if l > 0 else i + l for l in ls]
+                if len(ls) > 1:
+                    ctot = sum(shape[l][0] for l in ls)
+                    for l in ls:
+                        if shape[l][0] % 8:
+                            raise NotImplementedError("concat source with channels % 8 != 0")
+                    buf = L.alloc_padded(batch, shape[i][1], shape[i][2], L.round_up(ctot, 64), device)
+                    off = 0
+                    for l in ls:
+                        target[l] = (buf, off)
+                        off += shape[l][0]
+                    views[i] = _View(buf, 0, ctot, shape[i][1], shape[i][2])
+
+        def out_view(layer):
+            cc, hh, ww = shape[layer]
+            if layer in target:
+                buf, off = target[layer]
+                return _View(buf, off, cc, hh, ww)
+            bn_ = 256 if cc > 128 else (128 if cc > 64 else 64)
+            return _View(L.alloc_padded(batch, hh, ww, L.round_up(cc, bn_), device), 0, cc, hh, ww)
+
+        steps = []
+        heads = []
+        i = 0
+        while i < n:
+            d = defs[i]
+            t = d["type"]
+            if t == "convolutional":
+                nxt = defs[i + 1]["type"] if i + 1 < n else None
+                cin = 3 if i == 0 else shape[i - 1][0] if defs[i - 1]["type"] != "yolo" else None
+                src = None if i == 0 else views[i - 1]
+                cout, oh, ow = shape[i]
+                k, s = int(d["size"]), int(d["stride"])
+                wt, scale, bias, slope = self._folded(i, device)
+                if i == 0:
+                    if not (k == 3 and s == 1 and wt.shape[1] == 3 and cout in (16, 32) and slope is not None):
+                        raise NotImplementedError("first layer must be 3x3/1 conv, 3 -> 16|32 channels, leaky")
+                    v = out_view(0)
+                    wf = (wt * scale.view(-1, 1, 1, 1)).contiguous() if scale is not None else wt.contiguous()
+                    steps.append(("first", dict(w=wf, b=bias.contiguous(), cout=cout, slope=slope, out=v)))
+                    views[0] = v
+                    i += 1
+                    continue
+                fuse_res = nxt == "shortcut" and i not in self.routes
+                fuse_up = nxt == "upsample" and i not in self.routes and int(defs[i + 1]["stride"]) == 2
+                is_head = nxt == "yolo"
+                mat = i + 1 if (fuse_res or fuse_up) else i       # the layer index whose output is materialised
+                desc = L.make_desc(batch, src.h, src.w, src.c, src.cs, cout, 0, k, s, slope is not None,
+                                   slope if slope is not None else 0.0, fuse_res, 0, fuse_up, is_head)
+                if src.c != wt.shape[1]:
+                    raise RuntimeError("channel mismatch at block %d" % i)
+                res = None
+                if is_head:
+                    out = torch.empty((batch, cout, oh, ow), dtype=torch.float32, device=device)
+                    out_ptr = out.data_ptr()
+                    heads.append((i, out))
+                else:
+                    v = out_view(mat)
+                    desc.cout_stride = v.cs
+                    out_ptr = v.ptr
+                    views[mat] = v
+                    views[i] = v if mat == i else None
+                    if fuse_res:
+                        frm = int(defs[i + 1]["from"])
+                        res = views[i + 1 + frm if frm < 0 else frm]
+                        if res is None or (res.c, res.h, res.w) != (cout, oh, ow):
+                            raise NotImplementedError("shortcut source layout")
+                        desc.res_stride = res.cs
+                pw = L.pack_weights(desc, wt, scale)
+                pb = L.padded_bias(desc, bias)
+                steps.append(("conv", dict(desc=desc, x=src.ptr, w=pw, b=pb, y=out_ptr,
+                                           r=res.ptr if res is not None else None,
+                                           keep=(src, res, views[mat] if not is_head else out))))
+                i += 2 if (fuse_res or fuse_up) else 1
+                continue
+            if t == "route":
+                ls = [int(x) for x in d["layers"].split(",")]
+                ls = [l if l > 0 else i + l for l in ls]
+                if len(ls) == 1:
+                    views[i] = views[ls[0]]
+                # multi-source: views[i] was set above and is filled by its producers
+            elif t == "yolo":
+                views[i] = None
+            elif t in ("shortcut", "upsample"):
+                raise NotImplementedError("%s at block %d does not follow a convolution it can be fused into" % (t, i))
+            i += 1
+        rows = [self.module_list[j].na * shape[j][1] * shape[j][2] for j in self.yolo_layers]
+        return dict(steps=steps, heads=heads, rows=rows, img=(height, width))
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward(self, x, var=None):
+        if self.training:
+            raise RuntimeError("rotate_yolov3_b200.Darknet: the training-mode path (batch-stat BN, dgrad/wgrad) is not "
+                               "built in this round; call .eval() -- there is no PyTorch fallback")
+        if not x.is_cuda:
+            raise RuntimeError("Darknet.forward needs a CUDA tensor (sm_100a kernels, no CPU fallback)")
+        x = x.float().contiguous()
+        b, _, h, w = x.shape
+        key = (b, h, w, x.device)
+        with torch.cuda.device(x.device):
+            if self._plan is None or self._plan_key != key:
+                self._plan = self._build_plan(b, h, w, x.device)
+                self._plan_key = key
+            plan = self._plan
+            lib = _lib.lib
+            stream = _lib.stream_ptr(x.device)
+            for kind, a in plan["steps"]:
+                if kind == "first":
+                    v = a["out"]
+                    st = lib.ryolo_conv_first_fwd(_lib.ptr(x), b, h, w, _lib.ptr(a["w"]), _lib.ptr(a["b"]), a["cout"],
+                                                  a["slope"], ctypes.c_void_p(v.ptr), v.cs, stream)
+                    _lib.check(st, "ryolo_conv_first_fwd")
+                else:
+                    st = lib.ryolo_conv_bn_act_fwd(ctypes.byref(a["desc"]), ctypes.c_void_p(a["x"]), _lib.ptr(a["w"]),
+                                                   _lib.ptr(a["b"]), ctypes.c_void_p(a["r"]) if a["r"] else None,
+                                                   ctypes.c_void_p(a["y"]), None, 0, stream)
+                    _lib.check(st, "ryolo_conv_bn_act_fwd")
+            nc = self.module_list[self.yolo_layers[0]].nc
+            total = sum(plan["rows"])
+            io = torch.empty((b, total, nc + 6), dtype=torch.float32, device=x.device)
+            ps = []
+            off = 0
+            for (ci, head), yi, r in zip(plan["heads"], self.yolo_layers, plan["rows"]):
+                ps.append(self.module_list[yi].decode_into(head, (h, w), io, total, off))
+                off += r
+        return io, tuple(ps)

@@ -286,6 +286,30 @@ def main():
     np.savez_compressed(os.path.join(HERE, "decode_golden.npz"), **dec)
     print("decode golden:", {k: v.shape for k, v in dec.items() if hasattr(v, "shape") and v.ndim > 1})
 
+    # ---- 6. whole-network eval forward of the reference Darknet (Darknet-53 graph of cfg/yolov3.cfg, 6 anchors) ----
+    import tempfile
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    sys.path.insert(0, REPO)
+    import helpers
+    spec = __import__("importlib.util").util.spec_from_file_location("cfgs", os.path.join(REPO, "rotate-yolov3_b200", "cfgs.py"))
+    cfgs = __import__("importlib.util").util.module_from_spec(spec)
+    spec.loader.exec_module(cfgs)
+    text = cfgs.yolov3_cfg(width=96, height=64, classes=1, anchors=helpers.SMALL_ANCHORS, n_anchors=6)
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(text)
+        cfg_path = f.name
+    model = rmodels.Darknet(cfg_path, {"context_factor": 1.0}, arc="default")
+    helpers.init_darknet_weights(model, seed=123)
+    model.eval()
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(2, 3, 64, 96, generator=g)
+    with torch.no_grad():
+        io, ps = model(x)
+    np.savez_compressed(os.path.join(HERE, "darknet_golden.npz"), x=x.numpy(), io=io.numpy(),
+                        p0=ps[0].numpy(), p1=ps[1].numpy(), p2=ps[2].numpy(), n_params=sum(p.numel() for p in model.parameters()))
+    print("darknet golden:", tuple(io.shape), [tuple(p.shape) for p in ps], float(io.abs().max()),
+          [float(p.abs().max()) for p in ps])
+
 
 if __name__ == "__main__":
     main()

@@ -107,3 +107,38 @@ def adversarial_dets(seed=7):
     nn_ = base[88:90].clone(); nn_[:, 0] = float("nan"); rows.append(nn_)
     b = torch.cat(rows, 0)
     return torch.cat([b, tie_free_scores(len(b), seed + 1)[:, None]], 1).contiguous()
+
+
+def init_darknet_weights(model, seed=0):
+    """Deterministic non-trivial parameters for a (reference or our) Darknet: He-scaled conv weights, randomised BN
+    affine + running statistics and PReLU slopes (defaults mu=0, var=1, slope=0.1 would hide folding bugs,
+    SURVEY.md 8d config 5).  Same CPU generator sequence on both sides -> identical weights by state_dict order."""
+    g = torch.Generator().manual_seed(seed)
+    sd = model.state_dict()
+    with torch.no_grad():
+        for name, t in sd.items():
+            if not t.is_floating_point():
+                continue
+            shp = tuple(t.shape)
+            if name.endswith("Conv2d.weight"):
+                fan_in = shp[1] * shp[2] * shp[3]
+                v = torch.randn(shp, generator=g) * (0.9 / fan_in) ** 0.5
+            elif name.endswith("Conv2d.bias"):
+                v = torch.randn(shp, generator=g) * 0.5
+            elif name.endswith("BatchNorm2d.weight"):
+                v = 0.6 + 0.8 * torch.rand(shp, generator=g)
+            elif name.endswith("BatchNorm2d.bias"):
+                v = 0.2 * torch.randn(shp, generator=g)
+            elif name.endswith("running_mean"):
+                v = 0.2 * torch.randn(shp, generator=g)
+            elif name.endswith("running_var"):
+                v = 0.5 + torch.rand(shp, generator=g)
+            elif name.endswith("activation.weight"):
+                v = 0.05 + 0.25 * torch.rand(shp, generator=g)
+            else:
+                v = torch.randn(shp, generator=g) * 0.1
+            t.copy_(v.to(t.device))
+    return model
+
+
+SMALL_ANCHORS = "ara 900, 5000 / 5.0 / -60, 0, 60"   # 6 anchors -> na = 2 per scale (reference 'ara' grammar)

@@ -1,0 +1,120 @@
+"""Whole-network eval forward of ``Darknet`` (Darknet-53 graph of cfg/yolov3.cfg) on the GPU.
+
+(1) vs the committed output of the REFERENCE model (tests/golden/make_golden.py section 6, CPU fp32): the conv
+    operands are bf16 (fp32 accumulate), so the comparison is at bf16 tolerance through 75 layers -- stated below;
+(2) vs a plain PyTorch fp32 emulation of the SAME quantisation points (operands rounded to bf16 at every layer
+    boundary, fp32 math): isolates kernel correctness from precision, much tighter."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import GOLDEN, SMALL_ANCHORS, init_darknet_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(width=96, height=64):
+    import rotate_yolov3_b200 as pkg
+    from rotate_yolov3_b200 import cfgs
+    text = cfgs.yolov3_cfg(width=width, height=height, classes=1, anchors=SMALL_ANCHORS, n_anchors=6)
+    m = pkg.Darknet(text, {"context_factor": 1.0}, arc="default")
+    init_darknet_weights(m, seed=123)
+    return m.cuda().eval()
+
+
+def _emulate_bf16(model, x):
+    """torch fp32 reference of the same op chain with bf16 operand rounding at the kernel's quantisation points"""
+    def q(t):
+        return t.to(torch.bfloat16).float()
+    outs = []
+    heads = []
+    for i, (d, mod) in enumerate(zip(model.module_defs, model.module_list)):
+        t = d["type"]
+        if t == "convolutional":
+            w, scale, bias, slope = model._folded(i, x.device)
+            wq = q(w * scale.view(-1, 1, 1, 1)) if scale is not None else q(w)
+            xin = x if i == 0 else q(x)
+            if i == 0:
+                wq = w * scale.view(-1, 1, 1, 1)           # first layer runs in fp32 on the CUDA cores
+            k = w.shape[-1]
+            y = F.conv2d(xin, wq, bias, stride=int(d["stride"]), padding=(k - 1) // 2)
+            if slope is not None:
+                y = torch.where(y > 0, y, slope * y)
+            x = y
+            if model.module_defs[i + 1]["type"] == "yolo":
+                heads.append(y)
+        elif t == "shortcut":
+            x = x + q(outs[i + int(d["from"])])
+        elif t == "upsample":
+            x = F.interpolate(x, scale_factor=2, mode="nearest")
+        elif t == "route":
+            ls = [int(v) for v in d["layers"].split(",")]
+            ls = [l if l > 0 else i + l for l in ls]
+            x = torch.cat([outs[l] for l in ls], 1) if len(ls) > 1 else outs[ls[0]]
+        outs.append(x)
+    return heads
+
+
+def test_vs_reference_model_output():
+    g = np.load(os.path.join(GOLDEN, "darknet_golden.npz"))
+    m = _model()
+    assert sum(p.numel() for p in m.parameters()) == int(g["n_params"])
+    with torch.no_grad():
+        io, ps = m(torch.from_numpy(g["x"]).cuda())
+    assert io.shape == g["io"].shape and len(ps) == 3
+    for k, p in enumerate(ps):
+        want = g["p%d" % k]
+        assert p.shape == want.shape
+        err = np.abs(p.cpu().numpy() - want)
+        scale = np.abs(want).max()
+        # bf16 operands (8-bit mantissa) through 75 layers vs the fp32 reference: 3e-2 of the output scale
+        assert err.max() <= 3e-2 * scale, (k, float(err.max()), float(scale))
+        assert np.sqrt((err ** 2).mean()) <= 6e-3 * scale
+    # decoded boxes: compare where exp() has not amplified the raw difference
+    io_want = g["io"]
+    xy_err = np.abs(io.cpu().numpy()[..., :2] - io_want[..., :2]).max()
+    assert xy_err <= 0.5, float(xy_err)        # pixels (stride 8..32 times a sigmoid difference)
+    assert np.abs(io.cpu().numpy()[..., 4:6] - io_want[..., 4:6]).max() <= 3e-2
+
+
+def test_vs_torch_emulation_of_the_same_quantisation():
+    m = _model()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 64, 96, generator=g).cuda()
+    with torch.no_grad():
+        io, ps = m(x)
+        heads = _emulate_bf16(m, x)
+    for p, hd, yi in zip(ps, heads, m.yolo_layers):
+        layer = m.module_list[yi]
+        want = hd.view(hd.shape[0], layer.na, layer.nc + 6, hd.shape[2], hd.shape[3]).permute(0, 1, 3, 4, 2)
+        err = (p - want).abs()
+        scale = float(want.abs().max())
+        # identical quantisation points; remaining differences = fp32 summation order flipping a bf16 rounding
+        # somewhere upstream (one bf16 ulp = 0.4 %), diluted by the following layers
+        assert float(err.max()) <= 1e-2 * scale, (float(err.max()), scale)
+        assert float(err.pow(2).mean().sqrt()) <= 1e-3 * scale
+
+
+def test_boundary_and_state_dict_names():
+    import rotate_yolov3_b200 as pkg
+    m = _model()
+    names = list(m.state_dict().keys())
+    assert "module_list.0.Conv2d.weight" in names and "module_list.0.BatchNorm2d.running_var" in names
+    assert "module_list.0.activation.weight" in names and "module_list.81.Conv2d.bias" in names
+    assert m.yolo_layers == [82, 94, 106] and len(m.module_list) == 107
+    assert set(m.routes) >= {79, 85, 61, 91, 97, 36}
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64))          # CPU tensor: no fallback
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64, device="cuda"))
+    m.eval()
+    with torch.no_grad():
+        io1, _ = m(torch.rand(1, 3, 64, 64, device="cuda"))
+        io2, _ = m(torch.rand(3, 3, 96, 64, device="cuda"))   # new shape -> new plan
+    assert io1.shape == (1, 2 * (4 + 16 + 64), 7) and io2.shape == (3, 2 * (6 + 24 + 96), 7)
+    yl = m.module_list[106]
+    assert (yl.nx, yl.ny) == (8, 12) and float(yl.stride) == 8.0 and yl.anchor_vec.shape == (2, 3)
