@@ -112,8 +112,9 @@ struct MaskSmem {
   float col[kGeomFields * TB];
   float scratch[3 * kMaxPts * MASK_THREADS];
   u64 mask[TB * CH];
-  unsigned short queue[TB * TB];
-  int cnt;
+  unsigned short queue[TB * TB];    // stage A1 survivors (bounding circles)
+  unsigned short queue2[TB * TB];   // stage A2 survivors (separating axes) = exact-path work list
+  int cnt, cnt2;
 };
 
 // Conservative "provably no intersection" test.  true => the exact path would find 0 candidate
@@ -161,45 +162,82 @@ __global__ void __launch_bounds__(MASK_THREADS) rnms_mask_kernel(const float* __
       const int f = e / TB, i = e % TB;
       sm.col[e] = geom[(size_t)f * n_pad + cbi * TB + i];
     }
-    if (tid == 0) sm.cnt = 0;
+    if (tid == 0) { sm.cnt = 0; sm.cnt2 = 0; }
     __syncthreads();
 
-    // ---- phase A: filter, compact survivors into the queue ----
+    // ---- stage A1: bounding circles, 16 pairs per thread, ONE compaction per thread ----
     {
       const float rcx = sm.row[F_CX * TB + r], rcy = sm.row[F_CY * TB + r], rrad = sm.row[F_RAD * TB + r];
-      const float rux = sm.row[F_UX * TB + r], ruy = sm.row[F_UY * TB + r];
-      const float rhw = sm.row[F_HW * TB + r], rhh = sm.row[F_HH * TB + r];
       const bool row_ok = rb * TB + r < n;
-#pragma unroll 4
-      for (int k = 0; k < 16; k++) {
-        const int c = g * 16 + k;
-        bool cand = row_ok && (cbi * TB + c < n) && (cbi > rb || c > r);
-        if (cand && use_filter) {
-          cand = !surely_disjoint(rcx, rcy, rrad, rux, ruy, rhw, rhh, sm.col[F_CX * TB + c], sm.col[F_CY * TB + c],
-                                  sm.col[F_RAD * TB + c], sm.col[F_UX * TB + c], sm.col[F_UY * TB + c],
-                                  sm.col[F_HW * TB + c], sm.col[F_HH * TB + c]);
+      unsigned pass = 0;
+      if (row_ok) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const int c = g * 16 + k;   // same column for the whole warp: shared-memory broadcast
+          bool cand = (cbi * TB + c < n) && (cbi > rb || c > r);
+          if (use_filter) {
+            const float dx = sm.col[F_CX * TB + c] - rcx, dy = sm.col[F_CY * TB + c] - rcy;
+            const float R = rrad + sm.col[F_RAD * TB + c];
+            cand = cand && !(dx * dx + dy * dy > R * R);
+          }
+          pass |= (cand ? 1u : 0u) << k;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m) {
+      }
+      const int cnt = __popc(pass);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      int base = 0;
+      if (lane == 31) base = atomicAdd(&sm.cnt, incl);
+      base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+      while (pass) {
+        const int k = __ffs(pass) - 1;
+        pass &= pass - 1;
+        sm.queue[base++] = (unsigned short)((r << 6) | (g * 16 + k));
+      }
+    }
+    __syncthreads();
+    // ---- stage A2: separating axes on the circle survivors, converged warps ----
+    {
+      const int cnt1 = sm.cnt;
+      for (int q0 = 0; q0 < cnt1; q0 += MASK_THREADS) {
+        const int q = q0 + tid;
+        bool keep = false;
+        int e = 0;
+        if (q < cnt1) {
+          e = sm.queue[q];
+          const int qr = e >> 6, qc = e & 63;
+          keep = !use_filter ||
+                 !surely_disjoint(sm.row[F_CX * TB + qr], sm.row[F_CY * TB + qr], sm.row[F_RAD * TB + qr],
+                                  sm.row[F_UX * TB + qr], sm.row[F_UY * TB + qr], sm.row[F_HW * TB + qr],
+                                  sm.row[F_HH * TB + qr], sm.col[F_CX * TB + qc], sm.col[F_CY * TB + qc],
+                                  sm.col[F_RAD * TB + qc], sm.col[F_UX * TB + qc], sm.col[F_UY * TB + qc],
+                                  sm.col[F_HW * TB + qc], sm.col[F_HH * TB + qc]);
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, keep);
+        if (mk) {
           int base = 0;
-          if (lane == 0) base = atomicAdd(&sm.cnt, __popc(m));
+          if (lane == 0) base = atomicAdd(&sm.cnt2, __popc(mk));
           base = __shfl_sync(0xffffffffu, base, 0);
-          if (cand) sm.queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)((r << 6) | c);
+          if (keep) sm.queue2[base + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)e;
         }
       }
     }
     __syncthreads();
 
-    // ---- phase B: exact overlap on the survivors, one pair per thread ----
+    // ---- stage B: exact overlap on the survivors, one pair per thread ----
     {
-      const int cnt = sm.cnt;
+      const int cnt = sm.cnt2;
       PtScratch sc;
       sc.x = sm.scratch + tid;
       sc.y = sm.scratch + kMaxPts * MASK_THREADS + tid;
       sc.k = sm.scratch + 2 * kMaxPts * MASK_THREADS + tid;
       sc.stride = MASK_THREADS;
       for (int q = tid; q < cnt; q += MASK_THREADS) {
-        const int e = sm.queue[q];
+        const int e = sm.queue2[q];
         const int qr = e >> 6, qc = e & 63;
         TileGeom g1{sm.row, qr}, g2{sm.col, qc};
         const float inter = exact_inter_area(g1, g2, sc);
@@ -216,66 +254,102 @@ __global__ void __launch_bounds__(MASK_THREADS) rnms_mask_kernel(const float* __
   }
 }
 
-// Greedy scan (reference host loop :358-376) + original-index compaction (:380-383), one CTA.
+// Greedy scan (reference host loop :358-376) + original-index compaction (:380-383), one CTA, software-pipelined:
+//   warp 0 is the serial critical path.  For block b it needs remv[b] = OR of the mask word b of every box kept so far.
+//   Contributions of blocks <= b-2 are accumulated into shared remv[] by the helper warps one iteration behind;
+//   the contribution of block b-1 comes from registers: warp 0 prefetches, one block ahead, the diagonal words
+//   (64 rows x word b) and the next-column words (64 rows x word b+1) of the block, so no global-memory latency sits
+//   on the chain -- only ~kept(b) iterations of {find-first-set, 64-bit shuffle, OR}.
+//   Helper warps (1..31), after the per-block barrier, OR the rows kept in block b into remv[j], j >= b+2, one warp
+//   per 32 consecutive columns (coalesced 256-byte row segments, up to 8 loads in flight per lane), while warp 0 is
+//   already resolving block b+1.
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
+  const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+  const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+  return ((u64)hi << 32) | lo;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __restrict__ mask, int n, int col_blocks,
                                                                  const int* __restrict__ order,
                                                                  unsigned char* __restrict__ keep_flag,
                                                                  long long* __restrict__ keep_out,
                                                                  int* __restrict__ num_keep) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* remv = reinterpret_cast<u64*>(smem_raw);  // [col_blocks]
-  __shared__ u64 s_kept;
+  u64* remv = reinterpret_cast<u64*>(smem_raw);   // [col_blocks]
+  u64* keptw = remv + col_blocks;                  // [col_blocks] kept bits per block
   __shared__ int s_warp_sums[SCAN_THREADS / 32];
   __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int j = tid; j < col_blocks; j += SCAN_THREADS) remv[j] = 0ull;
   __syncthreads();
 
+  auto ld = [&](int row, int word) -> u64 {
+    return (row < n && word < col_blocks) ? mask[(size_t)row * col_blocks + word] : 0ull;
+  };
+  u64 dg0 = 0, dg1 = 0, nx0 = 0, nx1 = 0, ext = 0;
+  if (warp == 0) {
+    dg0 = ld(lane, 0); dg1 = ld(lane + 32, 0);
+    nx0 = ld(lane, 1); nx1 = ld(lane + 32, 1);
+  }
   for (int b = 0; b < col_blocks; b++) {
     if (warp == 0) {
-      const int row0 = b * TB + lane, row1 = row0 + 32;
-      const u64 d0 = row0 < n ? mask[(size_t)row0 * col_blocks + b] : 0ull;
-      const u64 d1 = row1 < n ? mask[(size_t)row1 * col_blocks + b] : 0ull;
-      u64 rm = remv[b];
-      u64 kept = 0ull;
+      const int r1 = (b + 1) * TB + lane;
+      const u64 pd0 = ld(r1, b + 1), pd1 = ld(r1 + 32, b + 1);   // consumed next iteration
+      const u64 pn0 = ld(r1, b + 2), pn1 = ld(r1 + 32, b + 2);
       const int nvalid = min(TB, n - b * TB);
-      for (int i = 0; i < nvalid; i++) {
-        const u64 di = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
-        if (!((rm >> i) & 1ull)) {
-          kept |= 1ull << i;
-          rm |= di;
+      const u64 valid = nvalid >= 64 ? ~0ull : ((1ull << nvalid) - 1ull);
+      u64 rm = remv[b] | ext;
+      u64 kept = 0ull;
+      u64 avail = ~rm & valid;
+      while (avail) {
+        const int i = __ffsll((long long)avail) - 1;
+        kept |= 1ull << i;
+        rm |= shfl_u64(i < 32 ? dg0 : dg1, i & 31);
+        avail = ~rm & valid & ~((2ull << i) - 1ull);
+      }
+      // contribution of this block's kept rows to column b+1, from the prefetched registers
+      const u64 x = (((kept >> lane) & 1ull) ? nx0 : 0ull) | (((kept >> (lane + 32)) & 1ull) ? nx1 : 0ull);
+      const unsigned xlo = __reduce_or_sync(0xffffffffu, (unsigned)x);
+      const unsigned xhi = __reduce_or_sync(0xffffffffu, (unsigned)(x >> 32));
+      ext = ((u64)xhi << 32) | xlo;
+      if (lane == 0) keptw[b] = kept;
+      dg0 = pd0; dg1 = pd1; nx0 = pn0; nx1 = pn1;
+    }
+    __syncthreads();
+    if (warp >= 1) {
+      const u64 kept = keptw[b];
+      const int first = b + 2;
+      for (int j0 = first + (warp - 1) * 32; j0 < col_blocks; j0 += (SCAN_THREADS / 32 - 1) * 32) {
+        const int j = j0 + lane;
+        if (j < col_blocks) {
+          u64 acc = 0ull;
+          u64 bits = kept;
+          const u64* base = mask + (size_t)b * TB * col_blocks + j;
+          while (bits) {
+            u64 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              v[u] = 0ull;
+              if (bits) {
+                const int i = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                v[u] = base[(size_t)i * col_blocks];
+              }
+            }
+            acc |= ((v[0] | v[1]) | (v[2] | v[3])) | ((v[4] | v[5]) | (v[6] | v[7]));
+          }
+          remv[j] |= acc;   // column j is owned by exactly one lane of one warp
         }
       }
-      if (lane == 0) s_kept = kept;
-      // mark kept boxes by ORIGINAL index
-      if ((kept >> lane) & 1ull) keep_flag[order[b * TB + lane]] = 1;
-      if ((kept >> (lane + 32)) & 1ull) keep_flag[order[b * TB + 32 + lane]] = 1;
     }
-    __syncthreads();
-    const u64 kept = s_kept;
-    // every later column word: OR in the rows of the boxes kept in this block
-    for (int j = b + 1 + tid; j < col_blocks; j += SCAN_THREADS) {
-      u64 acc = 0ull;
-      u64 bits = kept;
-      const u64* base = mask + (size_t)b * TB * col_blocks + j;
-      while (bits) {
-        // up to 4 independent loads in flight
-        u64 v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-        int i0 = __ffsll((long long)bits) - 1; bits &= bits - 1;
-        v0 = base[(size_t)i0 * col_blocks];
-        if (bits) { int i1 = __ffsll((long long)bits) - 1; bits &= bits - 1; v1 = base[(size_t)i1 * col_blocks]; }
-        if (bits) { int i2 = __ffsll((long long)bits) - 1; bits &= bits - 1; v2 = base[(size_t)i2 * col_blocks]; }
-        if (bits) { int i3 = __ffsll((long long)bits) - 1; bits &= bits - 1; v3 = base[(size_t)i3 * col_blocks]; }
-        acc |= (v0 | v1) | (v2 | v3);
-      }
-      remv[j] |= acc;
-    }
-    __syncthreads();
   }
-
-  // compaction over ORIGINAL indices, ascending
+  __syncthreads();
+  // flag kept boxes by ORIGINAL index
+  for (int i = tid; i < n; i += SCAN_THREADS)
+    if ((keptw[i >> 6] >> (i & 63)) & 1ull) keep_flag[order[i]] = 1;
   if (tid == 0) s_base = 0;
   __syncthreads();
+  // compaction over ORIGINAL indices, ascending
   for (int start = 0; start < n; start += SCAN_THREADS) {
     const int i = start + tid;
     const int flag = (i < n) ? (int)keep_flag[i] : 0;
@@ -399,7 +473,7 @@ extern "C" int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out
     RYOLO_LAUNCH_CHECK();
   }
   {
-    const size_t smem = (size_t)p.col_blocks * sizeof(u64);
+    const size_t smem = (size_t)p.col_blocks * sizeof(u64) * 2;
     if (smem > 200 * 1024) {
       set_err("ryolo_rnms: n=%d too large for the single-CTA scan (col_blocks=%d)", n, p.col_blocks);
       return RYOLO_E_UNSUPPORTED;
