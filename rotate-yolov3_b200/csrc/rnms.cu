@@ -134,7 +134,7 @@ __device__ __forceinline__ bool surely_disjoint(float rcx, float rcy, float rrad
   return false;
 }
 
-__global__ void __launch_bounds__(MASK_THREADS) rnms_mask_kernel(const float* __restrict__ geom, int n, int n_pad,
+__global__ void __launch_bounds__(MASK_THREADS, 3) rnms_mask_kernel(const float* __restrict__ geom, int n, int n_pad,
                                                                  int col_blocks, float thr, int use_filter,
                                                                  u64* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
