@@ -175,6 +175,18 @@ int ryolo_conv_first_fwd(const float* img, int batch, int h, int w, const float*
                          const float* bias, int cout, float slope, void* y, int cout_stride,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------ *
+ * Training path of the conv blocks (reference: autograd through nn.Conv2d / BatchNorm2d / PReLU,
+ * train.py:268-282).  Same padded-NHWC bf16 layout; gradients of activations are bf16, gradients
+ * of parameters fp32.
+ * ------------------------------------------------------------------------------------------ */
+/* dW[tap][co][ci] (fp32, [k*k][cout_pad][cin_pad], ACCUMULATED into a caller-zeroed buffer) =
+ * sum over flat padded pixels p of dz[p, co] * x[p + tap_offset, ci].  dz / x: padded NHWC bf16 at
+ * the conv's INPUT resolution (a stride-2 conv passes its output gradient zero-inserted onto the
+ * input grid).  tcgen05 GEMM with K = pixels, MN-major operands, split-K + fp32 atomics. */
+int ryolo_conv_wgrad(const void* dz, int dz_cstride, int cout_pad, const void* x, int x_cstride,
+                     int cin_pad, int batch, int in_h, int in_w, int ksize, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,3 +112,39 @@ def test_first_layer_direct_conv():
     assert bool(((got - want).abs() <= 2.0 ** -8 * want.abs() + 1e-5).all())
     assert float(y[..., 32:].abs().max()) == 0      # channel padding zeroed for the next layer's 64-wide K chunk
     assert float(y[:, 0].abs().max()) == 0 and float(y[:, :, 0].abs().max()) == 0
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(batch=2, h=19, w=19, cin=64, cout=64, k=3),
+    dict(batch=2, h=19, w=19, cin=128, cout=256, k=3),
+    dict(batch=3, h=38, w=38, cin=256, cout=128, k=1),
+    dict(batch=1, h=20, w=16, cin=32, cout=64, k=3),        # channel padding on the K... N side (cin 32 -> 64)
+    dict(batch=2, h=19, w=19, cin=768, cout=256, k=1),      # cin_pad 768 = 3 n-tiles of 256
+    dict(batch=4, h=38, w=38, cin=128, cout=504, k=1),      # cout_pad 512
+])
+def test_conv_wgrad_vs_torch(cfg):
+    """tcgen05 wgrad (K = pixels, MN-major operands, split-K atomics) vs torch.nn.grad.conv2d_weight in fp32 on the
+    same bf16-representable operands; tolerance 2e-3 of the gradient scale (fp32 atomics reorder the split-K sum)."""
+    import ctypes
+    import rotate_yolov3_b200 as pkg
+    from rotate_yolov3_b200 import layout as L
+    b, h, w, cin, cout, k = (cfg[n] for n in ("batch", "h", "w", "cin", "cout", "k"))
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(b, cin, h, w, generator=g).to(dev).to(torch.bfloat16).float()
+    dz = torch.randn(b, cout, h, w, generator=g).to(dev).to(torch.bfloat16).float()
+    cin_pad = L.round_up(cin, 64)
+    bn = 256 if cout > 128 else (128 if cout > 64 else 64)
+    cout_pad = L.round_up(cout, bn)
+    xb = L.to_padded_nhwc(x, cin_pad)
+    dzb = L.to_padded_nhwc(dz, cout_pad)
+    dw = torch.zeros((k * k, cout_pad, cin_pad), dtype=torch.float32, device=dev)
+    st = pkg._lib.lib.ryolo_conv_wgrad(pkg._lib.ptr(dzb), cout_pad, cout_pad, pkg._lib.ptr(xb), cin_pad, cin_pad, b, h, w, k,
+                                       pkg._lib.ptr(dw), pkg._lib.stream_ptr(dev))
+    assert st == 0, pkg._lib.last_error()
+    torch.cuda.synchronize()
+    want = torch.nn.grad.conv2d_weight(x, (cout, cin, k, k), dz, stride=1, padding=(k - 1) // 2)
+    got = dw.view(k, k, cout_pad, cin_pad)[:, :, :cout, :cin].permute(2, 3, 0, 1)
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-3 * scale, (float((got - want).abs().max()), scale)
+    assert float(dw.view(k, k, cout_pad, cin_pad)[:, :, cout:].abs().max() if cout_pad > cout else 0.0) == 0.0
