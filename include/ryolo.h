@@ -187,6 +187,35 @@ int ryolo_conv_first_fwd(const float* img, int batch, int h, int w, const float*
 int ryolo_conv_wgrad(const void* dz, int dz_cstride, int cout_pad, const void* x, int x_cstride,
                      int cin_pad, int batch, int in_h, int in_w, int ksize, float* dw, void* stream);
 
+/* Per-channel batch statistics of a raw conv output z (padded NHWC bf16, interior pixels):
+ * sums[0..c) = sum z, sums[c..2c) = sum z^2 (fp32; zeroed inside). */
+int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, int w, int c, float* sums,
+                   void* stream);
+/* y = prelu(z * scale + shift) [+ residual], scale/shift = folded batch-stat BN (gamma*invstd,
+ * beta - mean*gamma*invstd); upsample2x writes every pixel to its 2x2 block of a 2h x 2w y. */
+int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, int w, int c,
+                     const float* scale, const float* shift, float slope, int has_act,
+                     const void* residual, int res_cstride, void* y, int y_cstride, int upsample2x,
+                     void* stream);
+/* Backward of the same block.  dy: gradient of y (at 2h x 2w when upsample2x).  z_dz: in = z, out =
+ * dz (gradient of the raw conv output, written in place).  sums (fp32 [2c+1], zeroed inside):
+ * [0..c) = d(beta), [c..2c) = d(gamma), [2c] = d(slope).  gres (optional): gradient buffer of the
+ * shortcut source, receives (+)= dy. */
+int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, void* z_dz, int z_cstride,
+                     int batch, int h, int w, int c, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, float slope, int has_act, int has_bn,
+                     float* sums, void* gres, int gres_cstride, int gres_accumulate, void* stream);
+/* Adjoint of a stride-2 conv's pixel selection: src (h x w) -> even interior pixels of the
+ * pre-zeroed dst (dst_h x dst_w). */
+int ryolo_zero_insert2x(const void* src, int src_cstride, int batch, int h, int w, int c, void* dst,
+                        int dst_cstride, int dst_h, int dst_w, void* stream);
+/* fp32 NCHW [B,C,H,W] -> bf16 padded NHWC interior, channels [0,C) (head gradients). */
+int ryolo_nchw_to_padded(const float* src, int batch, int c, int h, int w, void* dst,
+                         int dst_cstride, void* stream);
+/* im2col of the 3-channel fp32 image for the first 3x3 conv: bf16 padded NHWC with 64 channels
+ * (27 real, column = c*9 + kh*3 + kw), so that the first layer runs on the same GEMM kernels. */
+int ryolo_im2col_first(const float* img, int batch, int h, int w, void* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,12 @@ SIGNATURES = {
     "ryolo_conv_bn_act_fwd": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ryolo_conv_first_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _f, _vp, _i, _vp]),
     "ryolo_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ryolo_bn_stats": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ryolo_bn_act_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "ryolo_bn_act_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "ryolo_zero_insert2x": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "ryolo_nchw_to_padded": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "ryolo_im2col_first": (_i, [_vp, _i, _i, _i, _vp, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)

@@ -49,6 +49,7 @@ struct ConvParams {
   int stride;         // 1 or 2
   int oh, ow;         // output spatial size (unpadded)
   int out_cs;         // channel stride of the output buffer
+  int store_cols;     // bf16 output: columns [0, store_cols) of the padded filter range are stored
   int res_cs;         // channel stride of the residual buffer
   int has_act, has_res, upsample2x, out_f32_nchw;
   float slope;
@@ -203,6 +204,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc_ld32(t_row + c0, v);
         tc_wait_ld();
         if (!valid) continue;
+        if (!p.out_f32_nchw && nt * BN + c0 >= p.store_cols) continue;   // narrower output buffer than the padded tile
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) {
@@ -462,7 +464,9 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   const ConvGeom g = conv_geom(d);
   RYOLO_ARG_CHECK(d->cin_stride >= g.cin_pad && d->cin_stride % 8 == 0);  // 64-wide K chunks read the channel padding
   RYOLO_ARG_CHECK(d->out_dtype == RYOLO_DT_BF16 || d->out_dtype == RYOLO_DT_F32);
-  if (d->out_dtype == RYOLO_DT_BF16) RYOLO_ARG_CHECK(d->cout_stride >= g.cout_pad && d->cout_stride % 8 == 0);
+  if (d->out_dtype == RYOLO_DT_BF16)
+    RYOLO_ARG_CHECK(d->cout_stride % 8 == 0 && (d->cout_stride >= g.cout_pad ||
+                                                 (d->cout_stride % 32 == 0 && d->cout_stride >= d->cout)));
   RYOLO_ARG_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
 
   ConvParams p;
@@ -481,6 +485,7 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   p.oh = d->stride == 2 ? (d->in_h + 1) / 2 : d->in_h;   // k=3,pad=1 (or k=1,pad=0) with stride 2: ceil(h/2)
   p.ow = d->stride == 2 ? (d->in_w + 1) / 2 : d->in_w;
   p.out_cs = d->cout_stride;
+  p.store_cols = d->cout_stride < g.cout_pad ? d->cout_stride : g.cout_pad;
   p.res_cs = d->res_stride;
   p.has_act = d->has_act;
   p.has_res = d->has_residual;

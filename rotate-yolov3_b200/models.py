@@ -11,8 +11,9 @@ What is kept from the reference so that train.py / test.py / detect.py see the s
   * YOLO layers expose ``ng, anchor_vec, anchor_wh, stride, nx, ny, na, nc`` (read by model/loss.py:172-174,313);
   * eval forward returns ``(io [B, sum(na*ny*nx), nc+6], (p0, p1, p2))`` with p_i = [B, na, ny, nx, nc+6].
 
-Scope of this round: the INFERENCE path (eval mode).  Training-mode forward (batch-statistics BN + backward) is the
-next row of SURVEY.md section 8 and raises until it is built -- there is no PyTorch fallback."""
+Eval mode: inference path above.  Training mode: ``forward`` returns the list of raw head tensors like the reference
+(models.py:192-194) and is differentiable -- forward with batch-statistics BatchNorm and the whole backward run on the
+same library (train_path.py).  There is no PyTorch fallback in either mode."""
 import ctypes
 
 import numpy as np
@@ -164,6 +165,8 @@ class Darknet(nn.Module):
         self.seen = np.array([0], dtype=np.int64)
         self._plan = None
         self._plan_key = None
+        self._tplan = None
+        self._tplan_key = None
 
     # ------------------------------------------------------------------------------------------------------
     def fuse(self):
@@ -320,14 +323,19 @@ class Darknet(nn.Module):
 
     # ------------------------------------------------------------------------------------------------------
     def forward(self, x, var=None):
-        if self.training:
-            raise RuntimeError("rotate_yolov3_b200.Darknet: the training-mode path (batch-stat BN, dgrad/wgrad) is not "
-                               "built in this round; call .eval() -- there is no PyTorch fallback")
         if not x.is_cuda:
             raise RuntimeError("Darknet.forward needs a CUDA tensor (sm_100a kernels, no CPU fallback)")
         x = x.float().contiguous()
         b, _, h, w = x.shape
         key = (b, h, w, x.device)
+        if self.training:
+            # reference models.py:192-194, 290-292: list of raw [B, na, ny, nx, nc+6] tensors; differentiable
+            from .train_path import DarknetTrainFn, TrainPlan
+            with torch.cuda.device(x.device):
+                if self._tplan is None or self._tplan_key != key:
+                    self._tplan = TrainPlan(self, b, h, w, x.device)
+                    self._tplan_key = key
+                return list(DarknetTrainFn.apply(self._tplan, x, *list(self.parameters())))
         with torch.cuda.device(x.device):
             if self._plan is None or self._plan_key != key:
                 self._plan = self._build_plan(b, h, w, x.device)

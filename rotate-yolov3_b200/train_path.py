@@ -1,0 +1,302 @@
+"""Training-mode execution of ``Darknet`` on libryolo.so: forward with batch-statistics BatchNorm and the full backward
+(reference: train.py:268-282 -- ``pred = model(imgs)``; ``loss.backward()`` through nn.Conv2d / BatchNorm2d / PReLU,
+shortcut, route, upsample).
+
+Per conv block:  z = conv(x, W) (tcgen05 implicit GEMM, raw, bf16)  ->  batch statistics (bn_stats)  ->
+y = prelu(z*scale + shift) [+ shortcut] [2x2 replicated] (bn_act_fwd).  Backward, in reverse:  bn_act_bwd (d-gamma,
+d-beta, d-slope, dz in place of z, shortcut gradient)  ->  wgrad (tcgen05 GEMM over pixels)  ->  dgrad (the SAME
+implicit-GEMM kernel as forward with the taps mirrored and the weight matrix transposed, accumulating into the
+source's gradient buffer through the kernel's residual input).  Stride-2 blocks run their adjoints on the input grid
+through a zero-inserted copy of dz.  The first layer (3 channels) goes through an im2col of the image so that it uses
+the same kernels.  Activations and activation gradients are bf16 (padded NHWC), parameter gradients fp32.
+
+The whole network is ONE autograd.Function: PyTorch's autograd sees the three head tensors on the outside (so the
+loss stays ordinary PyTorch, reference model/loss.py) and receives the parameter gradients in ``parameters()`` order."""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import layout as L
+
+_EPS = 1e-5
+
+
+class _Block:
+    pass
+
+
+class TrainPlan:
+    def __init__(self, model, batch, height, width, device):
+        self.model, self.batch, self.h, self.w, self.device = model, batch, height, width, device
+        defs = model.module_defs
+        n = len(defs)
+        shape = [None] * n
+        c, h, w = 3, height, width
+        for i, d in enumerate(defs):
+            t = d["type"]
+            if t == "convolutional":
+                s = int(d["stride"])
+                c, h, w = int(d["filters"]), (h + s - 1) // s, (w + s - 1) // s
+            elif t == "upsample":
+                h, w = h * int(d["stride"]), w * int(d["stride"])
+            elif t == "route":
+                ls = [l if l > 0 else i + l for l in (int(x) for x in d["layers"].split(","))]
+                c = sum(shape[l][0] for l in ls)
+                h, w = shape[ls[0]][1], shape[ls[0]][2]
+            elif t not in ("shortcut", "yolo"):
+                raise NotImplementedError("block type %r has no training kernel" % t)
+            shape[i] = (c, h, w)
+        self.shape = shape
+
+        # activation buffers (y) and their gradient twins; concat groups share one buffer
+        target = {}
+        views = [None] * n
+        gviews = [None] * n
+
+        def alloc_pair(hh, ww, cs):
+            return L.alloc_padded(batch, hh, ww, cs, device), L.alloc_padded(batch, hh, ww, cs, device)
+
+        for i, d in enumerate(defs):
+            if d["type"] == "route":
+                ls = [l if l > 0 else i + l for l in (int(x) for x in d["layers"].split(","))]
+                if len(ls) > 1:
+                    ctot = sum(shape[l][0] for l in ls)
+                    buf, gbuf = alloc_pair(shape[i][1], shape[i][2], L.round_up(ctot, 64))
+                    off = 0
+                    for l in ls:
+                        target[l] = (buf, gbuf, off)
+                        off += shape[l][0]
+                    views[i] = _mk_view(buf, 0, ctot, shape[i][1], shape[i][2])
+                    gviews[i] = _mk_view(gbuf, 0, ctot, shape[i][1], shape[i][2])
+
+        def out_views(layer):
+            cc, hh, ww = shape[layer]
+            if layer in target:
+                buf, gbuf, off = target[layer]
+            else:
+                bn_ = 256 if cc > 128 else (128 if cc > 64 else 64)
+                buf, gbuf = alloc_pair(hh, ww, L.round_up(cc, bn_))
+                off = 0
+            return _mk_view(buf, off, cc, hh, ww), _mk_view(gbuf, off, cc, hh, ww)
+
+        # first layer input: im2col of the image (27 real channels in a 64-channel padded NHWC buffer)
+        self.col = L.alloc_padded(batch, height, width, 64, device)
+        blocks = []
+        i = 0
+        while i < n:
+            d = defs[i]
+            t = d["type"]
+            if t == "convolutional":
+                nxt = defs[i + 1]["type"] if i + 1 < n else None
+                blk = _Block()
+                blk.i = i
+                blk.k, blk.stride = int(d["size"]), int(d["stride"])
+                seq = model.module_list[i]
+                blk.has_bn = hasattr(seq, "BatchNorm2d")
+                blk.has_act = hasattr(seq, "activation")
+                blk.cout, blk.oh, blk.ow = shape[i]
+                if i == 0:
+                    if not (blk.k == 3 and blk.stride == 1):
+                        raise NotImplementedError("first layer must be 3x3 stride 1")
+                    blk.src = _mk_view(self.col, 0, 27, height, width)
+                    blk.gsrc = None
+                    blk.k_eff = 1                       # runs as a 1x1 conv over the im2col buffer
+                else:
+                    blk.src, blk.gsrc = views[i - 1], gviews[i - 1]
+                    blk.k_eff = blk.k
+                blk.fuse_res = nxt == "shortcut" and i not in model.routes
+                blk.fuse_up = nxt == "upsample" and i not in model.routes and int(defs[i + 1]["stride"]) == 2
+                blk.is_head = nxt == "yolo"
+                blk.mat = i + 1 if (blk.fuse_res or blk.fuse_up) else i
+                bn_ = 256 if blk.cout > 128 else (128 if blk.cout > 64 else 64)
+                blk.cout_pad = L.round_up(blk.cout, bn_)
+                blk.cin = blk.src.c
+                blk.cin_pad = L.round_up(blk.cin, 64)
+                if blk.is_head:
+                    blk.out = torch.empty((batch, blk.cout, blk.oh, blk.ow), dtype=torch.float32, device=device)
+                    blk.dz = L.alloc_padded(batch, blk.oh, blk.ow, blk.cout_pad, device)   # gradient of the head output
+                    blk.res = blk.gres = None
+                else:
+                    blk.z = L.alloc_padded(batch, blk.oh, blk.ow, blk.cout_pad, device)     # raw conv output / dz
+                    blk.y, blk.gy = out_views(blk.mat)
+                    views[blk.mat], gviews[blk.mat] = blk.y, blk.gy
+                    if blk.fuse_res:
+                        frm = int(defs[i + 1]["from"])
+                        ridx = i + 1 + frm if frm < 0 else frm
+                        blk.res, blk.gres = views[ridx], gviews[ridx]
+                    else:
+                        blk.res = blk.gres = None
+                    blk.sums = torch.zeros(2 * blk.cout, dtype=torch.float32, device=device)
+                    blk.bsums = torch.zeros(2 * blk.cout + 1, dtype=torch.float32, device=device)
+                if blk.stride == 2:
+                    blk.dz_up = L.alloc_padded(batch, blk.src.h, blk.src.w, blk.cout_pad, device)  # zero-inserted dz
+                blk.dw = torch.zeros((blk.k_eff * blk.k_eff, blk.cout_pad, blk.cin_pad), dtype=torch.float32, device=device)
+                # forward descriptor: raw conv (no bias / activation); heads keep their bias and write fp32 NCHW
+                blk.fdesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cin, blk.src.cs, blk.cout,
+                                        0 if blk.is_head else blk.cout_pad, blk.k_eff, blk.stride, False, 0.0, False, 0,
+                                        False, blk.is_head)
+                if i > 0:
+                    # dgrad: stride-1 conv of dz (at the INPUT resolution) with mirrored taps / transposed weights
+                    blk.ddesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cout, blk.cout_pad, blk.cin, blk.gsrc.cs,
+                                            blk.k, 1, False, 0.0, False, blk.gsrc.cs, False, False)
+                blocks.append(blk)
+                i += 2 if (blk.fuse_res or blk.fuse_up) else 1
+                continue
+            if t == "route":
+                ls = [l if l > 0 else i + l for l in (int(x) for x in d["layers"].split(","))]
+                if len(ls) == 1:
+                    views[i], gviews[i] = views[ls[0]], gviews[ls[0]]
+            elif t in ("shortcut", "upsample"):
+                raise NotImplementedError("%s at block %d does not follow a convolution it can be fused into" % (t, i))
+            i += 1
+        self.blocks = blocks
+        self.zero_bias = torch.zeros(2048, dtype=torch.float32, device=device)
+        # static accumulate flags for the backward writers (first writer of a gradient range overwrites)
+        written = {}
+
+        def claim(view):
+            key = view.buf.data_ptr()
+            lo, hi = view.ch_off, view.ch_off + view.c
+            covered = any(a <= lo and hi <= b for a, b in written.get(key, []))
+            written.setdefault(key, []).append((lo, hi))
+            return covered
+        for blk in reversed(blocks):
+            blk.gres_acc = claim(blk.gres) if blk.gres is not None else False
+            blk.gsrc_acc = claim(blk.gsrc) if blk.gsrc is not None else False
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward(self, x):
+        m = self.model
+        lib = _lib.lib
+        st = _lib.stream_ptr(self.device)
+        _lib.check(lib.ryolo_im2col_first(_lib.ptr(x), self.batch, self.h, self.w, _lib.ptr(self.col), st), "im2col")
+        n_per_pixel = float(self.batch)
+        heads = []
+        # all PReLU slopes in ONE device->host transfer (they are kernel scalars)
+        act_blocks = [b for b in self.blocks if b.has_act]
+        if act_blocks:
+            vals = torch.cat([m.module_list[b.i].activation.weight.detach().float().reshape(1) for b in act_blocks]).tolist()
+            for b, v in zip(act_blocks, vals):
+                b.slope = float(v)
+        for blk in self.blocks:
+            seq = m.module_list[blk.i]
+            w = seq.Conv2d.weight.detach()
+            if blk.i == 0:
+                w = w.reshape(blk.cout, 27, 1, 1)
+            blk.pw = L.pack_weights(blk.fdesc, w)
+            if blk.is_head:
+                bias = L.padded_bias(blk.fdesc, seq.Conv2d.bias.detach())
+                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.fdesc), ctypes.c_void_p(blk.src.ptr), _lib.ptr(blk.pw),
+                                                     _lib.ptr(bias), None, _lib.ptr(blk.out), None, 0, st), "conv head")
+                heads.append(blk)
+                continue
+            _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.fdesc), ctypes.c_void_p(blk.src.ptr), _lib.ptr(blk.pw),
+                                                 _lib.ptr(self.zero_bias), None, _lib.ptr(blk.z), None, 0, st), "conv")
+            cnt = n_per_pixel * blk.oh * blk.ow
+            if blk.has_bn:
+                bn = seq.BatchNorm2d
+                _lib.check(lib.ryolo_bn_stats(_lib.ptr(blk.z), blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout,
+                                              _lib.ptr(blk.sums), st), "bn_stats")
+                mean = blk.sums[:blk.cout] / cnt
+                var = (blk.sums[blk.cout:] / cnt - mean * mean).clamp_(min=0.0)
+                invstd = torch.rsqrt(var + bn.eps)
+                gamma, beta = bn.weight.detach().float(), bn.bias.detach().float()
+                blk.scale = (gamma * invstd).contiguous()
+                blk.shift = (beta - mean * blk.scale).contiguous()
+                blk.mean, blk.invstd = mean.contiguous(), invstd.contiguous()
+                with torch.no_grad():      # running statistics, momentum 0.1, unbiased variance (nn.BatchNorm2d)
+                    mom = bn.momentum
+                    bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+                    bn.running_var.mul_(1 - mom).add_(var * (cnt / max(cnt - 1.0, 1.0)), alpha=mom)
+                    bn.num_batches_tracked += 1
+            else:
+                raise NotImplementedError("conv block without BatchNorm that is not a YOLO head")
+            if not blk.has_act:
+                blk.slope = 1.0
+            _lib.check(lib.ryolo_bn_act_fwd(_lib.ptr(blk.z), blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout,
+                                            _lib.ptr(blk.scale), _lib.ptr(blk.shift), blk.slope, int(blk.has_act),
+                                            ctypes.c_void_p(blk.res.ptr) if blk.res is not None else None,
+                                            blk.res.cs if blk.res is not None else 0, ctypes.c_void_p(blk.y.ptr), blk.y.cs,
+                                            int(blk.fuse_up), st), "bn_act_fwd")
+        outs = []
+        for blk, yi in zip(heads, m.yolo_layers):
+            layer = m.module_list[yi]
+            if (layer.nx, layer.ny) != (blk.ow, blk.oh):
+                layer.create_grids((self.h, self.w), (blk.ow, blk.oh), self.device, torch.float32)
+            outs.append(blk.out.view(self.batch, layer.na, layer.nc + 6, blk.oh, blk.ow).permute(0, 1, 3, 4, 2).contiguous())
+        self.heads = heads
+        return outs
+
+    # ------------------------------------------------------------------------------------------------------
+    def backward(self, grads):
+        m = self.model
+        lib = _lib.lib
+        st = _lib.stream_ptr(self.device)
+        pgrads = {}
+        for blk, g, yi in zip(self.heads, grads, m.yolo_layers):
+            layer = m.module_list[yi]
+            g_nchw = g.permute(0, 1, 4, 2, 3).reshape(self.batch, blk.cout, blk.oh, blk.ow).contiguous().float()
+            pgrads[(blk.i, "Conv2d.bias")] = g_nchw.sum((0, 2, 3))
+            _lib.check(lib.ryolo_nchw_to_padded(_lib.ptr(g_nchw), self.batch, blk.cout, blk.oh, blk.ow, _lib.ptr(blk.dz),
+                                                blk.cout_pad, st), "nchw_to_padded")
+        for blk in reversed(self.blocks):
+            seq = m.module_list[blk.i]
+            if blk.is_head:
+                dz = blk.dz
+            else:
+                _lib.check(lib.ryolo_bn_act_bwd(ctypes.c_void_p(blk.gy.ptr), blk.gy.cs, int(blk.fuse_up), _lib.ptr(blk.z),
+                                                blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout, _lib.ptr(blk.scale),
+                                                _lib.ptr(blk.shift), _lib.ptr(blk.mean), _lib.ptr(blk.invstd), blk.slope,
+                                                int(blk.has_act), 1, _lib.ptr(blk.bsums),
+                                                ctypes.c_void_p(blk.gres.ptr) if blk.gres is not None else None,
+                                                blk.gres.cs if blk.gres is not None else 0, int(blk.gres_acc), st),
+                           "bn_act_bwd")
+                pgrads[(blk.i, "BatchNorm2d.bias")] = blk.bsums[:blk.cout].clone()
+                pgrads[(blk.i, "BatchNorm2d.weight")] = blk.bsums[blk.cout:2 * blk.cout].clone()
+                if blk.has_act:
+                    pgrads[(blk.i, "activation.weight")] = blk.bsums[2 * blk.cout:].clone()
+                dz = blk.z
+            if blk.stride == 2:
+                _lib.check(lib.ryolo_zero_insert2x(_lib.ptr(dz), blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout_pad,
+                                                   _lib.ptr(blk.dz_up), blk.cout_pad, blk.src.h, blk.src.w, st), "zero_insert")
+                dz = blk.dz_up
+            blk.dw.zero_()
+            _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.cout_pad, blk.cout_pad, ctypes.c_void_p(blk.src.ptr), blk.src.cs,
+                                            blk.cin_pad, self.batch, blk.src.h, blk.src.w, blk.k_eff, _lib.ptr(blk.dw), st),
+                       "wgrad")
+            k = blk.k_eff
+            gw = blk.dw.view(k, k, blk.cout_pad, blk.cin_pad)[:, :, :blk.cout, :blk.cin].permute(2, 3, 0, 1)
+            pgrads[(blk.i, "Conv2d.weight")] = gw.reshape(seq.Conv2d.weight.shape).clone()
+            if blk.i > 0:
+                w = seq.Conv2d.weight.detach()
+                wd = w.flip(2, 3).permute(1, 0, 2, 3).contiguous()        # [cin, cout, k, k], taps mirrored
+                pwd = L.pack_weights(blk.ddesc, wd)
+                gp = blk.gsrc.ptr
+                blk.ddesc.has_residual = int(blk.gsrc_acc)
+                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(pwd),
+                                                     _lib.ptr(self.zero_bias), ctypes.c_void_p(gp) if blk.gsrc_acc else None,
+                                                     ctypes.c_void_p(gp), None, 0, st), "dgrad")
+        out = []
+        for name, p in m.named_parameters():
+            parts = name.split(".")            # module_list.{i}.{Module}.{param}
+            out.append(pgrads.get((int(parts[1]), parts[2] + "." + parts[3])))
+        return out
+
+
+def _mk_view(buf, ch_off, c, h, w):
+    from .models import _View
+    return _View(buf, ch_off, c, h, w)
+
+
+class DarknetTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, x, *params):
+        ctx.plan = plan
+        outs = plan.forward(x)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        pg = ctx.plan.backward([g.contiguous() for g in grads])
+        return (None, None) + tuple(pg)

@@ -310,6 +310,43 @@ def main():
     print("darknet golden:", tuple(io.shape), [tuple(p.shape) for p in ps], float(io.abs().max()),
           [float(p.abs().max()) for p in ps])
 
+    # ---- 7. training-mode forward + backward of the reference Darknet (batch-statistics BN, autograd) ----
+    text = cfgs.yolov3_cfg(width=160, height=128, classes=1, anchors=helpers.SMALL_ANCHORS, n_anchors=6)
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(text)
+        cfg_path = f.name
+    model = rmodels.Darknet(cfg_path, {"context_factor": 1.0}, arc="default")
+    helpers.init_darknet_weights(model, seed=321)
+    model.train()
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(4, 3, 128, 160, generator=g)
+    ps = model(x)
+    gs = [torch.randn(p.shape, generator=g) for p in ps]
+    loss = sum((p * gg).sum() for p, gg in zip(ps, gs)) / 100.0
+    loss.backward()
+    sav = {"x": x.numpy(), "loss": float(loss)}
+    for k_, (p, gg) in enumerate(zip(ps, gs)):
+        sav["p%d" % k_] = p.detach().numpy()
+        sav["g%d" % k_] = gg.numpy()
+    names, norms, samples, sample_idx = [], [], [], []
+    gi = torch.Generator().manual_seed(12)
+    for name, prm in model.named_parameters():
+        gflat = prm.grad.reshape(-1)
+        idx = torch.randint(0, gflat.numel(), (min(256, gflat.numel()),), generator=gi)
+        names.append(name)
+        norms.append(float(gflat.norm()))
+        sample_idx.append(idx.numpy())
+        samples.append(gflat[idx].numpy())
+    sav["names"] = np.array(names)
+    sav["norms"] = np.array(norms)
+    sav["sample_idx"] = np.array(sample_idx, dtype=object)
+    sav["samples"] = np.array(samples, dtype=object)
+    sav["rm0"] = model.module_list[0].BatchNorm2d.running_mean.numpy()
+    sav["rv0"] = model.module_list[0].BatchNorm2d.running_var.numpy()
+    sav["rm75"] = model.module_list[75].BatchNorm2d.running_mean.numpy()
+    np.savez_compressed(os.path.join(HERE, "darknet_train_golden.npz"), **sav)
+    print("train golden: loss %.4f, %d params, grad norm range %.3e .. %.3e" % (float(loss), len(names), min(norms), max(norms)))
+
 
 if __name__ == "__main__":
     main()

@@ -108,10 +108,6 @@ def test_boundary_and_state_dict_names():
     assert set(m.routes) >= {79, 85, 61, 91, 97, 36}
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 64, 64))          # CPU tensor: no fallback
-    m.train()
-    with pytest.raises(RuntimeError):
-        m(torch.zeros(1, 3, 64, 64, device="cuda"))
-    m.eval()
     with torch.no_grad():
         io1, _ = m(torch.rand(1, 3, 64, 64, device="cuda"))
         io2, _ = m(torch.rand(3, 3, 96, 64, device="cuda"))   # new shape -> new plan
