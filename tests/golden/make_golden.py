@@ -345,6 +345,32 @@ def main():
     sav["rv0"] = model.module_list[0].BatchNorm2d.running_var.numpy()
     sav["rm75"] = model.module_list[75].BatchNorm2d.running_mean.numpy()
     np.savez_compressed(os.path.join(HERE, "darknet_train_golden.npz"), **sav)
+
+    # ---- 8. the same on the 19-block "mini" graph (tight wiring check: few layers, little bf16 noise) ----
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(helpers.mini_cfg(64, 48))
+        cfg_path = f.name
+    mm = rmodels.Darknet(cfg_path, {"context_factor": 1.0}, arc="default")
+    helpers.init_darknet_weights(mm, seed=77)
+    g = torch.Generator().manual_seed(21)
+    xm = torch.rand(4, 3, 48, 64, generator=g)
+    mm.eval()
+    with torch.no_grad():
+        io_e, ps_e = mm(xm)
+    mm.train()
+    psm = mm(xm)
+    gsm = [torch.randn(p.shape, generator=g) for p in psm]
+    lm = sum((p * gg).sum() for p, gg in zip(psm, gsm)) / 10.0
+    lm.backward()
+    savm = {"x": xm.numpy(), "io_eval": io_e.numpy(), "loss": float(lm)}
+    for k_, (p, gg, pe) in enumerate(zip(psm, gsm, ps_e)):
+        savm["p%d" % k_] = p.detach().numpy()
+        savm["g%d" % k_] = gg.numpy()
+        savm["pe%d" % k_] = pe.numpy()
+    for name, prm in mm.named_parameters():
+        savm["grad:" + name] = prm.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "mini_train_golden.npz"), **savm)
+    print("mini golden: loss %.4f, %d grads" % (float(lm), len([k for k in savm if k.startswith("grad:")])))
     print("train golden: loss %.4f, %d params, grad norm range %.3e .. %.3e" % (float(loss), len(names), min(norms), max(norms)))
 
 

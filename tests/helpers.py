@@ -142,3 +142,21 @@ def init_darknet_weights(model, seed=0):
 
 
 SMALL_ANCHORS = "ara 900, 5000 / 5.0 / -60, 0, 60"   # 6 anchors -> na = 2 per scale (reference 'ara' grammar)
+
+
+def mini_cfg(width=64, height=48):
+    """A 19-block graph with every structural feature of cfg/yolov3.cfg (stride-2 convs, shortcuts, a route alias, an
+    upsample, a 2-source concat whose second source also feeds a stride-2 conv, two YOLO heads) but only 13 convs, so
+    that bf16 noise does not swamp a wiring check.  Reference 'ara' anchor grammar."""
+    def conv(f, k, s=1, bn=1, act="leaky"):
+        return "[convolutional]\n%sfilters=%d\nsize=%d\nstride=%d\npad=1\nactivation=%s\n\n" % (
+            "batch_normalize=1\n" if bn else "", f, k, s, act)
+    def yolo(lo, hi):
+        return "[yolo]\nmask = %d-%d\nanchors = %s\nclasses=1\nnum=6\n\n" % (lo, hi, SMALL_ANCHORS)
+    s = "[net]\nwidth=%d\nheight=%d\nchannels=3\n\n" % (width, height)
+    s += conv(32, 3) + conv(64, 3, 2) + conv(32, 1) + conv(64, 3) + "[shortcut]\nfrom=-3\nactivation=linear\n\n"
+    s += conv(128, 3, 2) + conv(64, 1) + conv(128, 3) + "[shortcut]\nfrom=-3\nactivation=linear\n\n"
+    s += conv(64, 1) + conv(21, 1, bn=0, act="linear") + yolo(3, 5)
+    s += "[route]\nlayers = -3\n\n" + conv(32, 1) + "[upsample]\nstride=2\n\n[route]\nlayers = -1, 4\n\n"
+    s += conv(64, 3) + conv(21, 1, bn=0, act="linear") + yolo(0, 2)
+    return s
