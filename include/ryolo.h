@@ -144,7 +144,8 @@ typedef struct ryolo_conv_desc {
   int32_t cin;         /* channels read by this conv                                          */
   int32_t cin_stride;  /* channel stride of the input buffer (>= round_up(cin, 64))           */
   int32_t cout;        /* filters                                                             */
-  int32_t cout_stride; /* channel stride of the bf16 output buffer (>= padded cout)           */
+  int32_t cout_stride; /* channel stride of the bf16 output buffer (>= round_up(cout, 32); channels
+                          [cout, round_up(cout,32)) are written as zeros, nothing beyond)     */
   int32_t ksize;       /* 1 or 3 (pad = (k-1)/2 as in models.py:53)                           */
   int32_t stride;      /* 1 or 2                                                              */
   int32_t has_act;     /* 1: PReLU with scalar `slope` (cfg activation=leaky), 0: linear      */

@@ -464,9 +464,7 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   const ConvGeom g = conv_geom(d);
   RYOLO_ARG_CHECK(d->cin_stride >= g.cin_pad && d->cin_stride % 8 == 0);  // 64-wide K chunks read the channel padding
   RYOLO_ARG_CHECK(d->out_dtype == RYOLO_DT_BF16 || d->out_dtype == RYOLO_DT_F32);
-  if (d->out_dtype == RYOLO_DT_BF16)
-    RYOLO_ARG_CHECK(d->cout_stride % 8 == 0 && (d->cout_stride >= g.cout_pad ||
-                                                 (d->cout_stride % 32 == 0 && d->cout_stride >= d->cout)));
+  if (d->out_dtype == RYOLO_DT_BF16) RYOLO_ARG_CHECK(d->cout_stride % 8 == 0 && d->cout_stride >= round_up(d->cout, 32));
   RYOLO_ARG_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
 
   ConvParams p;
@@ -485,7 +483,7 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   p.oh = d->stride == 2 ? (d->in_h + 1) / 2 : d->in_h;   // k=3,pad=1 (or k=1,pad=0) with stride 2: ceil(h/2)
   p.ow = d->stride == 2 ? (d->in_w + 1) / 2 : d->in_w;
   p.out_cs = d->cout_stride;
-  p.store_cols = d->cout_stride < g.cout_pad ? d->cout_stride : g.cout_pad;
+  p.store_cols = round_up(d->cout, 32);   // never touch channels beyond the 32-column chunk that holds the last filter
   p.res_cs = d->res_stride;
   p.has_act = d->has_act;
   p.has_res = d->has_residual;

@@ -53,7 +53,7 @@ def _run(batch, h, w, cin, cout, k, stride=1, act=True, residual=False, up=False
     else:
         y = L.alloc_padded(batch, oh * (2 if up else 1), ow * (2 if up else 1), cout_cs, dev)
         if cout_extra:
-            y[:, 1:-1, 1:-1, cout_pad:] = 3.0
+            y[:, 1:-1, 1:-1, (cout + 31) // 32 * 32:] = 3.0
     L.conv_fwd(desc, xb.data_ptr(), pw, pb, y.data_ptr(), res_buf.data_ptr() if residual else None, dev)
     torch.cuda.synchronize()
     want = _ref(x, wt, bias, stride, slope, act, res_t, up)
@@ -70,10 +70,10 @@ def _run(batch, h, w, cin, cout, k, stride=1, act=True, residual=False, up=False
         # halo untouched (zero), channel padding zero, neighbours of a wider buffer untouched
         assert float(y[:, 0].abs().max()) == 0 and float(y[:, -1].abs().max()) == 0
         assert float(y[:, :, 0].abs().max()) == 0 and float(y[:, :, -1].abs().max()) == 0
-        if cout_pad > cout:
-            assert float(y[:, 1:-1, 1:-1, cout:cout_pad].abs().max()) == 0
+        if cout_pad > cout and not cout_extra:
+            assert float(y[:, 1:-1, 1:-1, cout:cout_pad].abs().max()) == 0     # zero-initialised, chunk-padded or untouched
         if cout_extra:
-            assert float((y[:, 1:-1, 1:-1, cout_pad:] - 3.0).abs().max()) == 0
+            assert float((y[:, 1:-1, 1:-1, (cout + 31) // 32 * 32:] - 3.0).abs().max()) == 0
     return err
 
 
@@ -88,6 +88,7 @@ def _run(batch, h, w, cin, cout, k, stride=1, act=True, residual=False, up=False
     dict(batch=2, h=38, w=38, cin=768, cout=256, k=1, cin_extra=0),                 # long K (12 chunks)
     dict(batch=2, h=19, w=19, cin=64, cout=32, k=1, cin_extra=128),                 # cout padded 32->64, wide input buffer
     dict(batch=1, h=19, w=19, cin=512, cout=1024, k=3),                             # 4 n-tiles x 72 k-steps
+    dict(batch=2, h=12, w=16, cin=64, cout=32, k=1, up=True, cout_extra=64),        # 32 filters at offset 0 of a wider (concat) buffer: neighbours intact
 ])
 def test_conv_block_vs_torch(cfg):
     _run(**cfg)
