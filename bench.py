@@ -134,13 +134,98 @@ def cpu_rnms(n, steps=1):
             "sample": "%d boxes (config-3 generator), thr 0.5, K=%d; upper-triangle IoU + reference serial scan" % (n, k)}, times
 
 
+def torch_port_forward(model, x, train):
+    """PyTorch restatement of the reference Darknet.forward graph walk (model/models.py:244-298) on the modules of
+    `model` (same names / shapes as the reference's): the CPU baseline of the conv stacks."""
+    import torch
+    import torch.nn.functional as F
+    outs, heads = [], []
+    for i, (d, mod) in enumerate(zip(model.module_defs, model.module_list)):
+        t = d["type"]
+        if t == "convolutional":
+            k = mod.Conv2d.weight.shape[-1]
+            y = F.conv2d(x, mod.Conv2d.weight, mod.Conv2d.bias, stride=int(d["stride"]), padding=(k - 1) // 2)
+            if hasattr(mod, "BatchNorm2d"):
+                bn = mod.BatchNorm2d
+                y = F.batch_norm(y, None if train else bn.running_mean, None if train else bn.running_var, bn.weight, bn.bias,
+                                 training=train, eps=bn.eps)
+            if hasattr(mod, "activation"):
+                y = F.prelu(y, mod.activation.weight)
+            x = y
+            if model.module_defs[i + 1]["type"] == "yolo":
+                heads.append(y)
+        elif t == "shortcut":
+            x = x + outs[i + int(d["from"])]
+        elif t == "upsample":
+            x = F.interpolate(x, scale_factor=2, mode="nearest")
+        elif t == "route":
+            ls = [l if l > 0 else i + l for l in (int(v) for v in d["layers"].split(","))]
+            x = torch.cat([outs[l] for l in ls], 1) if len(ls) > 1 else outs[ls[0]]
+        outs.append(x)
+    res = []
+    for hd, yi in zip(heads, model.yolo_layers):
+        layer = model.module_list[yi]
+        res.append(hd.view(hd.shape[0], layer.na, layer.nc + 6, hd.shape[2], hd.shape[3]).permute(0, 1, 3, 4, 2).contiguous())
+    return res
+
+
+TRAIN_HYP = {"giou": 0.1, "cls": 27.76, "cls_pw": 1.0, "obj": 20.35, "obj_pw": 1.0, "iou_t": 0.5, "ang_t": 3.1415926 / 12,
+             "reg": 1.0, "context_factor": 1.0}    # cfg/hyp_template.py with cls_pw = obj_pw = 1 (arc 'default', train.py:43-45)
+
+
+def make_targets(n_img, seed):
+    """3 boxes / image: (img, 0, cx,cy~U(.1,.9), w~U(.05,.35), h = w/U(3,9), theta~U(-pi/2,pi/2))"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    nt = 3 * n_img
+    t = torch.zeros(nt, 7)
+    t[:, 0] = torch.arange(n_img).repeat_interleave(3).float()
+    t[:, 2:4] = 0.1 + 0.8 * torch.rand(nt, 2, generator=g)
+    t[:, 4] = 0.05 + 0.30 * torch.rand(nt, generator=g)
+    t[:, 5] = t[:, 4] / (3 + 6 * torch.rand(nt, generator=g))
+    t[:, 6] = (torch.rand(nt, generator=g) - 0.5) * math.pi
+    return t
+
+
+def cpu_train(steps=1, batch=2):
+    """fwd + loss + bwd of the same graph with stock PyTorch CPU kernels (what the reference's nn.Modules would run)"""
+    import torch
+    import helpers
+    import rotate_yolov3_b200 as pkg
+    from rotate_yolov3_b200 import cfgs
+    from rotate_yolov3_b200.loss import compute_loss
+    model = pkg.Darknet(cfgs.yolov3_cfg(), dict(TRAIN_HYP), arc="default")
+    helpers.init_darknet_weights(model, seed=1)
+    model.nc, model.hyp = 1, dict(TRAIN_HYP)
+    x = torch.rand(batch, 3, 608, 608)
+    tg = make_targets(batch, 5)
+    for yi in model.yolo_layers:
+        pass
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ps = torch_port_forward(model, x, True)
+        for p, yi in zip(ps, model.yolo_layers):
+            layer = model.module_list[yi]
+            if (layer.nx, layer.ny) != (p.shape[3], p.shape[2]):
+                layer.create_grids((608, 608), (p.shape[3], p.shape[2]), "cpu", torch.float32)
+        loss, _ = compute_loss(ps, tg.clone(), model, model.hyp)
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+        for p in model.parameters():
+            p.grad = None
+    return {"value": batch / min(times), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d images 608x608, fwd + compute_loss + bwd, stock PyTorch CPU kernels on the same graph "
+                      "(the reference's own model cannot be imported on the GPU box)" % batch}, times
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="riou", choices=["riou", "rnms", "detect"])
+    ap.add_argument("--workload", default="riou", choices=["riou", "rnms", "detect", "train"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads summary in the default run")
@@ -151,7 +236,7 @@ def main():
     K, W = args.steps, max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     metric = {"riou": ("rotated-IoU Mpairs/sec", "Mpairs/s"), "rnms": ("RNMS boxes/sec", "boxes/s"),
-              "detect": ("608x608 images/sec", "images/s")}[args.workload]
+              "detect": ("608x608 images/sec", "images/s"), "train": ("608x608 images/sec", "images/s")}[args.workload]
 
     if args.impl == "reference":
         # reference arm: the reference's own CPU implementation of the path on the host cores, rank 0 only
@@ -163,6 +248,9 @@ def main():
         elif args.workload == "rnms":
             cb, times = cpu_rnms(20000, steps=max(1, min(K, 2)))
             workload = "rotated NMS (config 3), the full 20000 boxes per step"
+        elif args.workload == "train":
+            cb, times = cpu_train(steps=max(1, min(K, 2)), batch=2)
+            workload = "Darknet-53 training step (config 4), bounded sample of 2 images per step"
         else:
             print(json.dumps({"impl": "reference", "unavailable": "detect workload has no CPU reference arm yet"}))
             return
@@ -239,6 +327,70 @@ def main():
         cfg = {"workload": "rotated NMS, 20000 boxes/image, 1 class, IoU thr 0.5 (BASELINE configs[2])",
                "sharding": "one image per rank (replicas), no collective",
                "l2": "50 MB mask rewritten every step; 192 MB flush buffer written between timed steps"}
+        scale = 1.0
+    elif args.workload == "train":
+        # BASELINE configs[3]: Darknet-53 training step, global batch 64 x 608 x 608 synthetic, compute_loss of the
+        # reference (no rotated IoU in it), SGD nesterov; images shard across ranks, per-replica BN, ONE
+        # NCCL all-reduce over the flattened gradients per step.
+        from rotate_yolov3_b200 import cfgs
+        from rotate_yolov3_b200.loss import compute_loss
+        per_gpu = max(1, 64 // world)
+        model = pkg.Darknet(cfgs.yolov3_cfg(), dict(TRAIN_HYP), arc="default")
+        helpers.init_darknet_weights(model, seed=1)
+        model.nc, model.hyp = 1, dict(TRAIN_HYP)
+        model = model.to(dev).train()
+        pg_w = [p for n, p in model.named_parameters() if "Conv2d.weight" in n]
+        pg_o = [p for n, p in model.named_parameters() if "Conv2d.weight" not in n]
+        opt = torch.optim.SGD([{"params": pg_o}, {"params": pg_w, "weight_decay": 4.569e-4}], lr=1e-4, momentum=0.97,
+                              nesterov=True)                       # train.py:70-82 param groups, cfg/hyp_template.py
+        x_h = torch.rand(per_gpu, 3, 608, 608, generator=torch.Generator().manual_seed(rank)).pin_memory()
+        tg_h = make_targets(per_gpu, 100 + rank).pin_memory()
+        x, tg = x_h.to(dev), tg_h.to(dev)
+        params = [p for p in model.parameters()]
+        units = per_gpu
+        alg_bytes = None
+        launches_per_step = 700
+        loss_h = torch.empty(1).pin_memory()
+        stage_ms = {}
+
+        def train_step(xd, td, timers=None):
+            opt.zero_grad(set_to_none=True)
+            if timers:
+                timers[0].record()
+            ps = model(xd)
+            if timers:
+                timers[1].record()
+            loss, items = compute_loss(ps, td.clone(), model, model.hyp)
+            loss.backward()
+            if timers:
+                timers[2].record()
+            if world > 1:
+                flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
+                dist.all_reduce(flat)
+                flat.div_(world)
+                for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
+                    p.grad.copy_(g)
+            opt.step()
+            if timers:
+                timers[3].record()
+            return loss
+
+        def step(i):
+            train_step(x, tg)
+
+        def step_e2e(i):
+            xd = x_h.to(dev, non_blocking=True)
+            td = tg_h.to(dev, non_blocking=True)
+            loss = train_step(xd, td)
+            loss_h.copy_(loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d, d2h = per_gpu * 3 * 608 * 608 * 4 + tg_h.numel() * 4, 4
+        cfg = {"workload": "Darknet-53 (cfg/yolov3.cfg graph) training step: fwd (batch-stat BN) + compute_loss + bwd + SGD, "
+                           "608x608 synthetic (BASELINE configs[3])",
+               "global_batch": per_gpu * world, "per_gpu_batch": per_gpu, "precision": "bf16 operands/activations, fp32 "
+               "accumulate and parameter gradients", "parallelism": "dp%d" % world,
+               "collective": "one NCCL all-reduce of 62.4M fp32 gradients per step (after backward, not yet overlapped)",
+               "l2": "activations of one step (tens of GB) exceed the 126 MB L2"}
         scale = 1.0
     else:
         # BASELINE configs[4] shape: eval forward (conv stacks + decode) -> conf filter -> per-image top-20000 -> RNMS.
@@ -360,6 +512,31 @@ def main():
         return
 
     # ---------------- roofline of the dominant kernel ----------------
+    if args.workload == "train":
+        tm = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        train_step(x, tg, tm)
+        torch.cuda.synchronize()
+        stage_ms = {"forward": tm[0].elapsed_time(tm[1]), "loss_backward": tm[1].elapsed_time(tm[2]),
+                    "allreduce_sgd": tm[2].elapsed_time(tm[3])}
+        flops = 3 * 141.98e9 * per_gpu                 # fwd + dgrad + wgrad, convs only
+        achieved_tf = flops / (ms_per_step * 1e-3) / 1e12
+        out = {"metric": metric[0], "value": value, "unit": metric[1], "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "bf16", "data": "synthetic", "config": cfg,
+               "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (fwd + dgrad) and conv_wgrad_kernel, whole step",
+                            "achieved": achieved_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": achieved_tf / pk["bf16_tflops_sustained"], "traffic": None,
+                            "peak_source": pk["src"] + " (sustained cuBLAS bf16)", "algorithmic_flops": flops,
+                            "stage_ms": stage_ms},
+               "e2e": {"value": e2e_val, "unit": metric[1], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": float(te.item())},
+               "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"], _ = cpu_train(steps=1, batch=2)
+        print(json.dumps(out))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "detect":
         tm = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         run(x, tm)
@@ -414,7 +591,8 @@ def main():
         # the other two metrics BASELINE.json names, measured by the same script in child processes AFTER the primary
         # measurement (summary only; run `bench.py --workload rnms|detect` for their full lines)
         also = {}
-        for wl, extra in (("rnms", ["--steps", "10", "--warmup", "3"]), ("detect", ["--steps", "3", "--warmup", "3"])):
+        for wl, extra in (("rnms", ["--steps", "10", "--warmup", "3"]), ("detect", ["--steps", "3", "--warmup", "3"]),
+                          ("train", ["--steps", "3", "--warmup", "3"])):
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--no-cpu-baseline"] + extra,
                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)

@@ -370,6 +370,33 @@ def main():
     for name, prm in mm.named_parameters():
         savm["grad:" + name] = prm.grad.numpy()
     np.savez_compressed(os.path.join(HERE, "mini_train_golden.npz"), **savm)
+
+    # ---- 9. reference compute_loss / build_targets (model/loss.py) on the section-7 model's training output ----
+    import model.loss as rloss
+    torch.Tensor.cuda = lambda self, *a, **k: self          # loss.py:197 hard-codes .cuda()
+    hyp_l = {"giou": 0.1, "cls": 27.76, "cls_pw": 1.0, "obj": 20.35, "obj_pw": 1.0, "iou_t": 0.5, "ang_t": 3.1415926 / 12,
+             "reg": 1.0, "context_factor": 1.0}
+    model.hyp, model.nc, model.arc = hyp_l, 1, "default"
+    g = torch.Generator().manual_seed(31)
+    nt = 9
+    tg = torch.zeros(nt, 7)
+    tg[:, 0] = torch.randint(0, 4, (nt,), generator=g).float()
+    tg[:, 2:4] = 0.1 + 0.8 * torch.rand(nt, 2, generator=g)
+    # sizes near the area-900 anchors (67 x 13.4 px on the 160 x 128 image) so that every GT is matched: the orphan-GT
+    # rescue (loss.py:235-242) indexes with a true-divided tensor, which the installed torch rejects
+    tg[:, 4] = (67.08 / 160.0) * (0.9 + 0.2 * torch.rand(nt, generator=g))
+    tg[:, 5] = (13.42 / 128.0) * (0.9 + 0.2 * torch.rand(nt, generator=g))
+    tg[:, 6] = torch.tensor([-0.8, -0.7, 0.75, 0.9, 0.6, -0.95, 0.8, -0.6, 0.7])[:nt]
+    pl = [p.detach().clone().requires_grad_(True) for p in ps]
+    loss_l, items = rloss.compute_loss(pl, tg.clone(), model, hyp_l)
+    loss_l.backward()
+    savl = {"targets": tg.numpy(), "loss": loss_l.detach().numpy(), "items": items.numpy(), "hyp_keys": np.array(list(hyp_l)),
+            "hyp_vals": np.array([hyp_l[k] for k in hyp_l])}
+    for k_, p in enumerate(pl):
+        savl["p%d" % k_] = p.detach().numpy()
+        savl["dp%d" % k_] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "loss_golden.npz"), **savl)
+    print("loss golden:", items.numpy())
     print("mini golden: loss %.4f, %d grads" % (float(lm), len([k for k in savm if k.startswith("grad:")])))
     print("train golden: loss %.4f, %d params, grad norm range %.3e .. %.3e" % (float(loss), len(names), min(norms), max(norms)))
 

@@ -141,7 +141,7 @@ def init_darknet_weights(model, seed=0):
     return model
 
 
-SMALL_ANCHORS = "ara 900, 5000 / 5.0 / -60, 0, 60"   # 6 anchors -> na = 2 per scale (reference 'ara' grammar)
+SMALL_ANCHORS = "ara 900, 3000, 9000 / 5.0 / -45, 45"   # 6 anchors: one area x 2 angles per scale (same angle set on every scale, as the reference loss assumes)
 
 
 def mini_cfg(width=64, height=48):
