@@ -192,6 +192,13 @@ int ryolo_conv_wgrad(const void* dz, int dz_cstride, int cout_pad, const void* x
  * sums[0..c) = sum z, sums[c..2c) = sum z^2 (fp32; zeroed inside). */
 int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, int w, int c, float* sums,
                    void* stream);
+/* sums -> per-channel mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, and (when the
+ * pointers are non-null) the nn.BatchNorm2d running statistics update with momentum and the
+ * unbiased variance (reference model/models.py:62: momentum 0.1, eps 1e-5). */
+int ryolo_bn_finalize(const float* sums, int c, float count, float eps, float momentum,
+                      const float* gamma, const float* beta, float* mean, float* invstd,
+                      float* scale, float* shift, float* running_mean, float* running_var,
+                      void* stream);
 /* y = prelu(z * scale + shift) [+ residual], scale/shift = folded batch-stat BN (gamma*invstd,
  * beta - mean*gamma*invstd); upsample2x writes every pixel to its 2x2 block of a 2h x 2w y. */
 int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, int w, int c,

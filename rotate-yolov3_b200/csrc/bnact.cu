@@ -33,10 +33,10 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 struct Geo {
-  int batch, h, w, c;   // interior size, real channels (multiple of 8)
+  int batch, h, w, c;   // interior size, real channels (multiple of 8; c/8 is a power of two for every Darknet width)
 };
 
-// thread -> (interior pixel, 8-channel group)
+// generic thread -> (interior pixel, 8-channel group) decode for the small layout kernels below
 __device__ __forceinline__ bool decode_item(const Geo& g, size_t item, int& b, int& y, int& x, int& cg) {
   const int cgs = g.c >> 3;
   const size_t npix = (size_t)g.batch * g.h * g.w;
@@ -52,28 +52,47 @@ __device__ __forceinline__ size_t pad_off(int b, int y, int x, int h, int w, int
   return (((size_t)b * (h + 2) + y + 1) * (w + 2) + x + 1) * cs;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, int zcs, Geo g,
-                                                       float* __restrict__ sums /*[2*c]*/, int items_per_block) {
-  extern __shared__ float s_acc[];  // [2 * c]
-  for (int i = threadIdx.x; i < 2 * g.c; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+// The four BN/PReLU kernels share one work decomposition: a CTA owns a contiguous span of interior ROWS (b, y);
+// thread t owns channel group (t mod cgs) for the whole kernel -- its 8 scale/shift/mean/invstd values live in
+// registers -- and walks the pixels of the span with stride blockDim/cgs.  No integer division in the inner loop
+// (cgs is a power of two), 16-byte accesses, consecutive threads on consecutive channel groups of the same pixel.
+constexpr int BNT = 256;
+
+struct RowSpan {
+  int cg, cgs_log2, px0, pstep;   // my channel group, log2(cgs), first pixel index within a row, pixel stride
+};
+__device__ __forceinline__ RowSpan row_span(const Geo& g) {
+  RowSpan r;
   const int cgs = g.c >> 3;
-  // a thread keeps its channel group for the whole block: items advance by a multiple of cgs
-  const int stride = (blockDim.x / cgs) * cgs;
-  const size_t begin = (size_t)blockIdx.x * items_per_block;
-  const size_t end = begin + items_per_block;
+  r.cgs_log2 = 31 - __clz(cgs);
+  r.cg = threadIdx.x & (cgs - 1);
+  r.px0 = threadIdx.x >> r.cgs_log2;
+  r.pstep = BNT >> r.cgs_log2;
+  return r;
+}
+__device__ __forceinline__ void load8(const float* __restrict__ p, int cg, float* o) {
+  const float4 a = *reinterpret_cast<const float4*>(p + cg * 8), b = *reinterpret_cast<const float4*>(p + cg * 8 + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BNT) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, int zcs, Geo g,
+                                                       float* __restrict__ sums /*[2*c]*/, int rows_per_block) {
+  extern __shared__ float s_acc[];  // [2 * c]
+  for (int i = threadIdx.x; i < 2 * g.c; i += BNT) s_acc[i] = 0.f;
+  __syncthreads();
+  const RowSpan rs = row_span(g);
+  const int nrows = g.batch * g.h;
+  const int row_begin = blockIdx.x * rows_per_block, row_end = min(nrows, row_begin + rows_per_block);
   float s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; e++) s1[e] = s2[e] = 0.f;
-  int cg_mine = -1;
-  if ((int)threadIdx.x < stride) {
-    for (size_t item = begin + threadIdx.x; item < end; item += stride) {
-      int b, y, x, cg;
-      if (!decode_item(g, item, b, y, x, cg)) break;
-      cg_mine = cg;
+  for (int row = row_begin; row < row_end; row++) {
+    const int b = row / g.h, y = row - b * g.h;
+    const __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, zcs) + rs.cg * 8;
+    for (int x = rs.px0; x < g.w; x += rs.pstep) {
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(z + pad_off(b, y, x, g.h, g.w, zcs) + cg * 8), f);
+      unpack8(*reinterpret_cast<const uint4*>(zr + (size_t)x * zcs), f);
 #pragma unroll
       for (int e = 0; e < 8; e++) {
         s1[e] += f[e];
@@ -81,52 +100,56 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
       }
     }
   }
-  if (cg_mine >= 0) {
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-      atomicAdd(&s_acc[cg_mine * 8 + e], s1[e]);
-      atomicAdd(&s_acc[g.c + cg_mine * 8 + e], s2[e]);
-    }
+  for (int e = 0; e < 8; e++) {
+    atomicAdd(&s_acc[rs.cg * 8 + e], s1[e]);
+    atomicAdd(&s_acc[g.c + rs.cg * 8 + e], s2[e]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * g.c; i += blockDim.x) atomicAdd(&sums[i], s_acc[i]);
+  for (int i = threadIdx.x; i < 2 * g.c; i += BNT) atomicAdd(&sums[i], s_acc[i]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int zcs, Geo g,
+__global__ void __launch_bounds__(BNT) bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int zcs, Geo g,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          float slope, int has_act, const __nv_bfloat16* __restrict__ res,
-                                                         int rcs, __nv_bfloat16* __restrict__ y, int ycs, int up) {
-  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int b, yy, xx, cg;
-  if (!decode_item(g, item, b, yy, xx, cg)) return;
-  float f[8];
-  unpack8(*reinterpret_cast<const uint4*>(z + pad_off(b, yy, xx, g.h, g.w, zcs) + cg * 8), f);
-  const float4 sc0 = *reinterpret_cast<const float4*>(scale + cg * 8), sc1 = *reinterpret_cast<const float4*>(scale + cg * 8 + 4);
-  const float4 sh0 = *reinterpret_cast<const float4*>(shift + cg * 8), sh1 = *reinterpret_cast<const float4*>(shift + cg * 8 + 4);
-  const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-  const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-  float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (res) unpack8(*reinterpret_cast<const uint4*>(res + pad_off(b, yy, xx, g.h, g.w, rcs) + cg * 8), r);
+                                                         int rcs, __nv_bfloat16* __restrict__ y, int ycs, int up,
+                                                         int rows_per_block) {
+  const RowSpan rs = row_span(g);
+  float sc[8], sh[8];
+  load8(scale, rs.cg, sc);
+  load8(shift, rs.cg, sh);
+  const int nrows = g.batch * g.h;
+  const int row_begin = blockIdx.x * rows_per_block, row_end = min(nrows, row_begin + rows_per_block);
+  for (int row = row_begin; row < row_end; row++) {
+    const int b = row / g.h, yy = row - b * g.h;
+    const __nv_bfloat16* zr = z + pad_off(b, yy, 0, g.h, g.w, zcs) + rs.cg * 8;
+    const __nv_bfloat16* rr = res ? res + pad_off(b, yy, 0, g.h, g.w, rcs) + rs.cg * 8 : nullptr;
+    for (int x = rs.px0; x < g.w; x += rs.pstep) {
+      float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      unpack8(*reinterpret_cast<const uint4*>(zr + (size_t)x * zcs), f);
+      if (rr) unpack8(*reinterpret_cast<const uint4*>(rr + (size_t)x * rcs), r);
 #pragma unroll
-  for (int e = 0; e < 8; e++) {
-    float u = fmaf(f[e], sc[e], sh[e]);
-    if (has_act) u = u > 0.f ? u : slope * u;
-    f[e] = u + r[e];
-  }
-  const uint4 o = pack8(f);
-  if (!up) {
-    *reinterpret_cast<uint4*>(y + pad_off(b, yy, xx, g.h, g.w, ycs) + cg * 8) = o;
-  } else {
+      for (int e = 0; e < 8; e++) {
+        float u = fmaf(f[e], sc[e], sh[e]);
+        if (has_act) u = u > 0.f ? u : slope * u;
+        f[e] = u + r[e];
+      }
+      const uint4 o = pack8(f);
+      if (!up) {
+        *reinterpret_cast<uint4*>(y + pad_off(b, yy, x, g.h, g.w, ycs) + rs.cg * 8) = o;
+      } else {
 #pragma unroll
-    for (int ry = 0; ry < 2; ry++)
+        for (int ry = 0; ry < 2; ry++)
 #pragma unroll
-      for (int rx = 0; rx < 2; rx++)
-        *reinterpret_cast<uint4*>(y + pad_off(b, 2 * yy + ry, 2 * xx + rx, 2 * g.h, 2 * g.w, ycs) + cg * 8) = o;
+          for (int rx = 0; rx < 2; rx++)
+            *reinterpret_cast<uint4*>(y + pad_off(b, 2 * yy + ry, 2 * x + rx, 2 * g.h, 2 * g.w, ycs) + rs.cg * 8) = o;
+      }
+    }
   }
 }
 
-// du for one 8-channel group; dy possibly at 2x resolution (sum of the 2x2 block = adjoint of nearest upsample)
+// dy for one 8-channel group; possibly at 2x resolution (sum of the 2x2 block = adjoint of nearest upsample)
 __device__ __forceinline__ void load_dy(const __nv_bfloat16* __restrict__ dy, int dcs, const Geo& g, int b, int y, int x,
                                         int cg, int up, float* d) {
   if (!up) {
@@ -146,104 +169,141 @@ __device__ __forceinline__ void load_dy(const __nv_bfloat16* __restrict__ dy, in
   }
 }
 
-__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, int up,
+__global__ void __launch_bounds__(BNT) bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, int up,
                                                                 const __nv_bfloat16* __restrict__ z, int zcs, Geo g,
                                                                 const float* __restrict__ scale,
                                                                 const float* __restrict__ shift,
                                                                 const float* __restrict__ mean,
                                                                 const float* __restrict__ invstd, float slope, int has_act,
                                                                 float* __restrict__ sums /*[2*c + 1]*/,
-                                                                int items_per_block) {
+                                                                int rows_per_block) {
   extern __shared__ float s_acc[];  // [2 * c + 1]
-  for (int i = threadIdx.x; i < 2 * g.c + 1; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * g.c + 1; i += BNT) s_acc[i] = 0.f;
   __syncthreads();
-  const int cgs = g.c >> 3;
-  const int stride = (blockDim.x / cgs) * cgs;
-  const size_t begin = (size_t)blockIdx.x * items_per_block;
-  const size_t end = begin + items_per_block;
+  const RowSpan rs = row_span(g);
+  float sc[8], sh[8], mu[8], is[8];
+  load8(scale, rs.cg, sc);
+  load8(shift, rs.cg, sh);
+  load8(mean, rs.cg, mu);
+  load8(invstd, rs.cg, is);
+  const int nrows = g.batch * g.h;
+  const int row_begin = blockIdx.x * rows_per_block, row_end = min(nrows, row_begin + rows_per_block);
   float a1[8], a2[8], asl = 0.f;
 #pragma unroll
   for (int e = 0; e < 8; e++) a1[e] = a2[e] = 0.f;
-  int cg_mine = -1;
-  if ((int)threadIdx.x < stride) {
-    for (size_t item = begin + threadIdx.x; item < end; item += stride) {
-      int b, y, x, cg;
-      if (!decode_item(g, item, b, y, x, cg)) break;
-      cg_mine = cg;
+  for (int row = row_begin; row < row_end; row++) {
+    const int b = row / g.h, y = row - b * g.h;
+    const __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, zcs) + rs.cg * 8;
+    for (int x = rs.px0; x < g.w; x += rs.pstep) {
       float f[8], d[8];
-      unpack8(*reinterpret_cast<const uint4*>(z + pad_off(b, y, x, g.h, g.w, zcs) + cg * 8), f);
-      load_dy(dy, dcs, g, b, y, x, cg, up, d);
+      unpack8(*reinterpret_cast<const uint4*>(zr + (size_t)x * zcs), f);
+      load_dy(dy, dcs, g, b, y, x, rs.cg, up, d);
 #pragma unroll
       for (int e = 0; e < 8; e++) {
-        const int ch = cg * 8 + e;
-        const float u = fmaf(f[e], scale[ch], shift[ch]);
+        const float u = fmaf(f[e], sc[e], sh[e]);
         float du = d[e];
         if (has_act && !(u > 0.f)) {
           asl = fmaf(d[e], u, asl);
           du *= slope;
         }
-        const float zh = (f[e] - mean[ch]) * invstd[ch];
+        const float zh = (f[e] - mu[e]) * is[e];
         a1[e] += du;
         a2[e] = fmaf(du, zh, a2[e]);
       }
     }
   }
-  if (cg_mine >= 0) {
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-      atomicAdd(&s_acc[cg_mine * 8 + e], a1[e]);
-      atomicAdd(&s_acc[g.c + cg_mine * 8 + e], a2[e]);
-    }
-    atomicAdd(&s_acc[2 * g.c], asl);
+  for (int e = 0; e < 8; e++) {
+    atomicAdd(&s_acc[rs.cg * 8 + e], a1[e]);
+    atomicAdd(&s_acc[g.c + rs.cg * 8 + e], a2[e]);
   }
+  // one slope atomic per warp
+  for (int o = 16; o > 0; o >>= 1) asl += __shfl_xor_sync(0xffffffffu, asl, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[2 * g.c], asl);
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * g.c + 1; i += blockDim.x) atomicAdd(&sums[i], s_acc[i]);
+  for (int i = threadIdx.x; i < 2 * g.c + 1; i += BNT) atomicAdd(&sums[i], s_acc[i]);
 }
 
-__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, int up,
+__global__ void __launch_bounds__(BNT) bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, int up,
                                                                __nv_bfloat16* __restrict__ z /*in: z, out: dz*/, int zcs,
                                                                Geo g, const float* __restrict__ scale,
                                                                const float* __restrict__ shift,
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ invstd, float slope, int has_act,
                                                                int has_bn, const float* __restrict__ sums, float inv_n,
-                                                               __nv_bfloat16* __restrict__ gres, int gcs, int gres_acc) {
-  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int b, y, x, cg;
-  if (!decode_item(g, item, b, y, x, cg)) return;
-  float f[8], d[8];
-  __nv_bfloat16* zp = z + pad_off(b, y, x, g.h, g.w, zcs) + cg * 8;
-  unpack8(*reinterpret_cast<const uint4*>(zp), f);
-  load_dy(dy, dcs, g, b, y, x, cg, up, d);
-  if (gres) {  // shortcut branch: d(residual) (+)= dy   (never combined with upsample)
-    __nv_bfloat16* gp = gres + pad_off(b, y, x, g.h, g.w, gcs) + cg * 8;
-    float o[8];
-    if (gres_acc) {
-      unpack8(*reinterpret_cast<const uint4*>(gp), o);
-#pragma unroll
-      for (int e = 0; e < 8; e++) o[e] += d[e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; e++) o[e] = d[e];
-    }
-    *reinterpret_cast<uint4*>(gp) = pack8(o);
-  }
-  float out[8];
+                                                               __nv_bfloat16* __restrict__ gres, int gcs, int gres_acc,
+                                                               int rows_per_block) {
+  const RowSpan rs = row_span(g);
+  float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+  load8(scale, rs.cg, sc);
+  load8(shift, rs.cg, sh);
+  load8(mean, rs.cg, mu);
+  load8(invstd, rs.cg, is);
+  load8(sums, rs.cg, m1);
+  load8(sums + g.c, rs.cg, m2);
 #pragma unroll
   for (int e = 0; e < 8; e++) {
-    const int ch = cg * 8 + e;
-    const float sc = scale[ch];
-    const float u = fmaf(f[e], sc, shift[ch]);
-    float du = d[e];
-    if (has_act && !(u > 0.f)) du *= slope;
-    if (has_bn) {
-      const float zh = (f[e] - mean[ch]) * invstd[ch];
-      out[e] = sc * (du - sums[ch] * inv_n - zh * sums[g.c + ch] * inv_n);
-    } else {
-      out[e] = du;
+    m1[e] *= inv_n;
+    m2[e] *= inv_n;
+  }
+  const int nrows = g.batch * g.h;
+  const int row_begin = blockIdx.x * rows_per_block, row_end = min(nrows, row_begin + rows_per_block);
+  for (int row = row_begin; row < row_end; row++) {
+    const int b = row / g.h, y = row - b * g.h;
+    __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, zcs) + rs.cg * 8;
+    __nv_bfloat16* gr = gres ? gres + pad_off(b, y, 0, g.h, g.w, gcs) + rs.cg * 8 : nullptr;
+    for (int x = rs.px0; x < g.w; x += rs.pstep) {
+      float f[8], d[8];
+      __nv_bfloat16* zp = zr + (size_t)x * zcs;
+      unpack8(*reinterpret_cast<const uint4*>(zp), f);
+      load_dy(dy, dcs, g, b, y, x, rs.cg, up, d);
+      if (gr) {  // shortcut branch: d(residual) (+)= dy   (never combined with upsample)
+        __nv_bfloat16* gp = gr + (size_t)x * gcs;
+        float o[8];
+        if (gres_acc) {
+          unpack8(*reinterpret_cast<const uint4*>(gp), o);
+#pragma unroll
+          for (int e = 0; e < 8; e++) o[e] += d[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e++) o[e] = d[e];
+        }
+        *reinterpret_cast<uint4*>(gp) = pack8(o);
+      }
+      float out[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const float u = fmaf(f[e], sc[e], sh[e]);
+        float du = d[e];
+        if (has_act && !(u > 0.f)) du *= slope;
+        out[e] = has_bn ? sc[e] * (du - m1[e] - (f[e] - mu[e]) * is[e] * m2[e]) : du;
+      }
+      *reinterpret_cast<uint4*>(zp) = pack8(out);
     }
   }
-  *reinterpret_cast<uint4*>(zp) = pack8(out);
+}
+
+// BN finalisation: sums -> mean, invstd, scale, shift, and the running statistics of nn.BatchNorm2d (momentum m, unbiased
+// variance), one thread per channel.  Replaces ~10 tiny framework launches per block.
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, int c, float count, float eps, float momentum,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ mean_o, float* __restrict__ invstd_o, float* __restrict__ scale_o,
+                                   float* __restrict__ shift_o, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const float mean = sums[ch] / count;
+  const float var = fmaxf(sums[c + ch] / count - mean * mean, 0.f);
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[ch] * invstd;
+  mean_o[ch] = mean;
+  invstd_o[ch] = invstd;
+  scale_o[ch] = sc;
+  shift_o[ch] = beta[ch] - mean * sc;
+  if (running_mean) {
+    running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -305,12 +365,24 @@ static inline Geo mk_geo(int batch, int h, int w, int c) {
   return g;
 }
 static inline size_t n_items(const Geo& g) { return (size_t)g.batch * g.h * g.w * (g.c >> 3); }
+// rows per CTA so that a CTA streams ~16k 16-byte items and the grid still has >= ~4 CTAs per SM
+static inline int rows_per_block(const Geo& g) {
+  const int cgs = g.c >> 3;
+  long long per_row = (long long)g.w * cgs;
+  int r = (int)((16384 + per_row - 1) / per_row);
+  const int nrows = g.batch * g.h;
+  const int max_r = (nrows + 591) / 592;
+  if (r > max_r) r = max_r;
+  return r < 1 ? 1 : r;
+}
+static inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 }  // namespace ryolo
 
 using namespace ryolo;
 
 #define GEO_CHECK() RYOLO_ARG_CHECK(batch > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && c <= 2048)
+#define GEO_CHECK_P2() RYOLO_ARG_CHECK(pow2(c >> 3))
 
 extern "C" int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, int w, int c, float* sums, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -318,12 +390,11 @@ extern "C" int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, in
   GEO_CHECK();
   const Geo g = mk_geo(batch, h, w, c);
   RYOLO_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, stream));
-  const size_t items = n_items(g);
-  const int cgs = c >> 3;
-  int per_block = ((256 / cgs) * cgs) * 64;
-  unsigned blocks = (unsigned)((items + per_block - 1) / per_block);
-  bn_stats_kernel<<<blocks, 256, 2 * c * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(z), z_cstride, g, sums,
-                                                                   per_block);
+  GEO_CHECK_P2();
+  const int rpb = rows_per_block(g);
+  const unsigned blocks = (unsigned)((batch * h + rpb - 1) / rpb);
+  bn_stats_kernel<<<blocks, BNT, 2 * c * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(z), z_cstride, g, sums,
+                                                                   rpb);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }
@@ -335,11 +406,12 @@ extern "C" int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, 
   RYOLO_ARG_CHECK(z && scale && shift && y);
   GEO_CHECK();
   RYOLO_ARG_CHECK(!(residual && upsample2x));
+  GEO_CHECK_P2();
   const Geo g = mk_geo(batch, h, w, c);
-  const size_t items = n_items(g);
-  bn_act_fwd_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(
+  const int rpb = rows_per_block(g);
+  bn_act_fwd_kernel<<<(unsigned)((batch * h + rpb - 1) / rpb), BNT, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(z), z_cstride, g, scale, shift, slope, has_act,
-      static_cast<const __nv_bfloat16*>(residual), res_cstride, static_cast<__nv_bfloat16*>(y), y_cstride, upsample2x);
+      static_cast<const __nv_bfloat16*>(residual), res_cstride, static_cast<__nv_bfloat16*>(y), y_cstride, upsample2x, rpb);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }
@@ -352,20 +424,32 @@ extern "C" int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, 
   RYOLO_ARG_CHECK(dy && z_dz && scale && shift && mean && invstd && sums);
   GEO_CHECK();
   RYOLO_ARG_CHECK(!(gres && upsample2x));
+  GEO_CHECK_P2();
   const Geo g = mk_geo(batch, h, w, c);
-  const size_t items = n_items(g);
   RYOLO_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * (2 * c + 1), stream));
-  const int cgs = c >> 3;
-  const int per_block = ((256 / cgs) * cgs) * 64;
-  bn_act_bwd_reduce_kernel<<<(unsigned)((items + per_block - 1) / per_block), 256, (2 * c + 1) * sizeof(float), stream>>>(
+  const int rpb = rows_per_block(g);
+  const unsigned blocks = (unsigned)((batch * h + rpb - 1) / rpb);
+  bn_act_bwd_reduce_kernel<<<blocks, BNT, (2 * c + 1) * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(dy), dy_cstride, upsample2x, static_cast<const __nv_bfloat16*>(z_dz), z_cstride, g,
-      scale, shift, mean, invstd, slope, has_act, sums, per_block);
+      scale, shift, mean, invstd, slope, has_act, sums, rpb);
   RYOLO_LAUNCH_CHECK();
   const float inv_n = 1.0f / ((float)batch * h * w);
-  bn_act_bwd_apply_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(
+  bn_act_bwd_apply_kernel<<<blocks, BNT, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(dy), dy_cstride, upsample2x, static_cast<__nv_bfloat16*>(z_dz), z_cstride, g, scale,
       shift, mean, invstd, slope, has_act, has_bn, sums, inv_n, static_cast<__nv_bfloat16*>(gres), gres_cstride,
-      gres_accumulate);
+      gres_accumulate, rpb);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_bn_finalize(const float* sums, int c, float count, float eps, float momentum, const float* gamma,
+                                 const float* beta, float* mean, float* invstd, float* scale, float* shift,
+                                 float* running_mean, float* running_var, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(sums && gamma && beta && mean && invstd && scale && shift && c > 0 && count > 0.f);
+  RYOLO_ARG_CHECK((running_mean == nullptr) == (running_var == nullptr));
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, c, count, eps, momentum, gamma, beta, mean, invstd, scale,
+                                                          shift, running_mean, running_var);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }

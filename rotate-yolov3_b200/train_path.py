@@ -128,6 +128,8 @@ class TrainPlan:
                     else:
                         blk.res = blk.gres = None
                     blk.sums = torch.zeros(2 * blk.cout, dtype=torch.float32, device=device)
+                    blk.mean, blk.invstd, blk.scale, blk.shift = (torch.zeros(blk.cout, dtype=torch.float32, device=device)
+                                                                  for _ in range(4))
                     blk.bsums = torch.zeros(2 * blk.cout + 1, dtype=torch.float32, device=device)
                 if blk.stride == 2:
                     blk.dz_up = L.alloc_padded(batch, blk.src.h, blk.src.w, blk.cout_pad, device)  # zero-inserted dz
@@ -179,6 +181,7 @@ class TrainPlan:
             vals = torch.cat([m.module_list[b.i].activation.weight.detach().float().reshape(1) for b in act_blocks]).tolist()
             for b, v in zip(act_blocks, vals):
                 b.slope = float(v)
+        bn_counters = []
         for blk in self.blocks:
             seq = m.module_list[blk.i]
             w = seq.Conv2d.weight.detach()
@@ -198,18 +201,11 @@ class TrainPlan:
                 bn = seq.BatchNorm2d
                 _lib.check(lib.ryolo_bn_stats(_lib.ptr(blk.z), blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout,
                                               _lib.ptr(blk.sums), st), "bn_stats")
-                mean = blk.sums[:blk.cout] / cnt
-                var = (blk.sums[blk.cout:] / cnt - mean * mean).clamp_(min=0.0)
-                invstd = torch.rsqrt(var + bn.eps)
-                gamma, beta = bn.weight.detach().float(), bn.bias.detach().float()
-                blk.scale = (gamma * invstd).contiguous()
-                blk.shift = (beta - mean * blk.scale).contiguous()
-                blk.mean, blk.invstd = mean.contiguous(), invstd.contiguous()
-                with torch.no_grad():      # running statistics, momentum 0.1, unbiased variance (nn.BatchNorm2d)
-                    mom = bn.momentum
-                    bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
-                    bn.running_var.mul_(1 - mom).add_(var * (cnt / max(cnt - 1.0, 1.0)), alpha=mom)
-                    bn.num_batches_tracked += 1
+                _lib.check(lib.ryolo_bn_finalize(_lib.ptr(blk.sums), blk.cout, cnt, bn.eps, bn.momentum, _lib.ptr(bn.weight),
+                                                 _lib.ptr(bn.bias), _lib.ptr(blk.mean), _lib.ptr(blk.invstd),
+                                                 _lib.ptr(blk.scale), _lib.ptr(blk.shift), _lib.ptr(bn.running_mean),
+                                                 _lib.ptr(bn.running_var), st), "bn_finalize")
+                bn_counters.append(bn.num_batches_tracked)
             else:
                 raise NotImplementedError("conv block without BatchNorm that is not a YOLO head")
             if not blk.has_act:
@@ -219,6 +215,9 @@ class TrainPlan:
                                             ctypes.c_void_p(blk.res.ptr) if blk.res is not None else None,
                                             blk.res.cs if blk.res is not None else 0, ctypes.c_void_p(blk.y.ptr), blk.y.cs,
                                             int(blk.fuse_up), st), "bn_act_fwd")
+        if bn_counters:
+            with torch.no_grad():
+                torch._foreach_add_(bn_counters, 1)
         outs = []
         for blk, yi in zip(heads, m.yolo_layers):
             layer = m.module_list[yi]
@@ -252,10 +251,10 @@ class TrainPlan:
                                                 ctypes.c_void_p(blk.gres.ptr) if blk.gres is not None else None,
                                                 blk.gres.cs if blk.gres is not None else 0, int(blk.gres_acc), st),
                            "bn_act_bwd")
-                pgrads[(blk.i, "BatchNorm2d.bias")] = blk.bsums[:blk.cout].clone()
-                pgrads[(blk.i, "BatchNorm2d.weight")] = blk.bsums[blk.cout:2 * blk.cout].clone()
+                pgrads[(blk.i, "BatchNorm2d.bias")] = blk.bsums[:blk.cout]
+                pgrads[(blk.i, "BatchNorm2d.weight")] = blk.bsums[blk.cout:2 * blk.cout]
                 if blk.has_act:
-                    pgrads[(blk.i, "activation.weight")] = blk.bsums[2 * blk.cout:].clone()
+                    pgrads[(blk.i, "activation.weight")] = blk.bsums[2 * blk.cout:]
                 dz = blk.z
             if blk.stride == 2:
                 _lib.check(lib.ryolo_zero_insert2x(_lib.ptr(dz), blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout_pad,
