@@ -56,13 +56,22 @@ uint64_t ryolo_launch_count(void);
  * the FMA contractions nvcc's default -fmad=true applies to it (DESIGN.md "pinned arithmetic"),
  * so the kept index list is bit-identical to the reference kernel's on the same inputs when the
  * scores are tie-free (the reference's torch sort is unstable; ours is a stable descending sort).
+ * The mask is evaluated lazily in row chunks of 1024 boxes, alternating with the greedy scan:
+ * rows and columns already suppressed by earlier chunks are skipped -- their mask bits can never
+ * influence the scan, so the kept list is unchanged while dense candidate sets cost far less.
  * Asynchronous on `stream`; no host synchronisation inside.
  * ------------------------------------------------------------------------------------------ */
 size_t ryolo_rnms_workspace_bytes(int n);
 int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep,
                void* workspace, size_t workspace_bytes, void* stream);
 
-/* Introspection of the last ryolo_rnms call that used `workspace` (valid until the workspace is
+/* Same result as ryolo_rnms, but computes EVERY upper-triangle mask word in one launch like the
+ * reference kernel (no skipping of already-suppressed rows/columns).  Slower; exists so that the
+ * parity tests can compare the whole mask with the reference's. */
+int ryolo_rnms_full_mask(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Introspection of the last ryolo_rnms_full_mask call that used `workspace` (valid until the workspace is
  * reused): device pointers to the score-sorted boxes [n,6], the sort permutation order[n]
  * (int32, sorted position -> original index) and the suppression mask [n, ceil(n/64)] uint64 in the
  * reference's layout (only words with column-block >= row-block are defined, as in the

@@ -41,6 +41,7 @@ SIGNATURES = {
     "ryolo_launch_count": (ctypes.c_uint64, []),
     "ryolo_rnms_workspace_bytes": (_sz, [_i]),
     "ryolo_rnms": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "ryolo_rnms_full_mask": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "ryolo_rnms_debug_views": (_i, [_vp, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "ryolo_riou_paired": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ryolo_riou_pairwise": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),

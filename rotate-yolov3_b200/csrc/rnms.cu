@@ -25,6 +25,7 @@ constexpr int TB = 64;            // boxes per tile side == bits per mask word (
 constexpr int CH = 8;             // column blocks handled per CTA
 constexpr int MASK_THREADS = 256;
 constexpr int SCAN_THREADS = 1024;
+constexpr int kRowChunkBlocks = 16;   // row blocks per lazy-mask chunk (1024 boxes)
 
 // field indices of the SoA geometry array geom[f * n_pad + i]
 enum {
@@ -134,14 +135,20 @@ __device__ __forceinline__ bool surely_disjoint(float rcx, float rcy, float rrad
   return false;
 }
 
+// `remv` (optional): suppression state at launch time (bit set = box already suppressed by a kept box of an earlier
+// row chunk).  Rows and columns that are already suppressed are skipped: their mask bits can never influence the
+// greedy scan (a suppressed row is never kept, so its mask row is never read; a suppressed column stays suppressed).
 __global__ void __launch_bounds__(MASK_THREADS, 3) rnms_mask_kernel(const float* __restrict__ geom, int n, int n_pad,
                                                                  int col_blocks, float thr, int use_filter,
-                                                                 u64* __restrict__ mask) {
+                                                                 u64* __restrict__ mask, int rb_begin,
+                                                                 const u64* __restrict__ remv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MaskSmem& sm = *reinterpret_cast<MaskSmem*>(smem_raw);
-  const int rb = blockIdx.y;
+  const int rb = rb_begin + blockIdx.y;
   const int cb0 = rb + blockIdx.x * CH;
   if (cb0 >= col_blocks) return;
+  const u64 row_dead = remv ? remv[rb] : 0ull;
+  if (row_dead == ~0ull) return;   // every row of this block is already suppressed: nothing it could contribute
   const int ncols = min(CH, col_blocks - cb0);
   const int tid = threadIdx.x;
 
@@ -157,6 +164,8 @@ __global__ void __launch_bounds__(MASK_THREADS, 3) rnms_mask_kernel(const float*
 
   for (int cc = 0; cc < ncols; cc++) {
     const int cbi = cb0 + cc;
+    const u64 col_dead = remv ? remv[cbi] : 0ull;
+    if (col_dead == ~0ull) continue;   // uniform for the CTA: whole column tile already suppressed
     __syncthreads();  // previous tile fully consumed (also covers the row-tile load on cc == 0)
     for (int e = tid; e < kGeomFields * TB; e += MASK_THREADS) {
       const int f = e / TB, i = e % TB;
@@ -168,13 +177,13 @@ __global__ void __launch_bounds__(MASK_THREADS, 3) rnms_mask_kernel(const float*
     // ---- stage A1: bounding circles, 16 pairs per thread, ONE compaction per thread ----
     {
       const float rcx = sm.row[F_CX * TB + r], rcy = sm.row[F_CY * TB + r], rrad = sm.row[F_RAD * TB + r];
-      const bool row_ok = rb * TB + r < n;
+      const bool row_ok = rb * TB + r < n && !((row_dead >> r) & 1ull);
       unsigned pass = 0;
       if (row_ok) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
           const int c = g * 16 + k;   // same column for the whole warp: shared-memory broadcast
-          bool cand = (cbi * TB + c < n) && (cbi > rb || c > r);
+          bool cand = (cbi * TB + c < n) && (cbi > rb || c > r) && !((col_dead >> c) & 1ull);
           if (use_filter) {
             const float dx = sm.col[F_CX * TB + c] - rcx, dy = sm.col[F_CY * TB + c] - rcy;
             const float R = rrad + sm.col[F_RAD * TB + c];
@@ -269,18 +278,26 @@ __device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
   return ((u64)hi << 32) | lo;
 }
 
+// Processes row blocks [b_begin, b_end) of the greedy scan; the suppression state `remv_g` and the kept bits `keptw_g`
+// live in global memory between launches (row chunks alternate with mask launches that skip what is already
+// suppressed).  The last launch (`final`) also compacts the kept ORIGINAL indices.
 __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __restrict__ mask, int n, int col_blocks,
                                                                  const int* __restrict__ order,
                                                                  unsigned char* __restrict__ keep_flag,
                                                                  long long* __restrict__ keep_out,
-                                                                 int* __restrict__ num_keep) {
+                                                                 int* __restrict__ num_keep, int b_begin, int b_end,
+                                                                 u64* __restrict__ remv_g, u64* __restrict__ keptw_g,
+                                                                 int final) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* remv = reinterpret_cast<u64*>(smem_raw);   // [col_blocks]
   u64* keptw = remv + col_blocks;                  // [col_blocks] kept bits per block
   __shared__ int s_warp_sums[SCAN_THREADS / 32];
   __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int j = tid; j < col_blocks; j += SCAN_THREADS) remv[j] = 0ull;
+  for (int j = tid; j < col_blocks; j += SCAN_THREADS) {
+    remv[j] = remv_g[j];
+    keptw[j] = keptw_g[j];
+  }
   __syncthreads();
 
   auto ld = [&](int row, int word) -> u64 {
@@ -288,10 +305,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __re
   };
   u64 dg0 = 0, dg1 = 0, nx0 = 0, nx1 = 0, ext = 0;
   if (warp == 0) {
-    dg0 = ld(lane, 0); dg1 = ld(lane + 32, 0);
-    nx0 = ld(lane, 1); nx1 = ld(lane + 32, 1);
+    const int r0 = b_begin * TB + lane;
+    dg0 = ld(r0, b_begin); dg1 = ld(r0 + 32, b_begin);
+    nx0 = ld(r0, b_begin + 1); nx1 = ld(r0 + 32, b_begin + 1);
   }
-  for (int b = 0; b < col_blocks; b++) {
+  for (int b = b_begin; b < b_end; b++) {
     if (warp == 0) {
       const int r1 = (b + 1) * TB + lane;
       const u64 pd0 = ld(r1, b + 1), pd1 = ld(r1 + 32, b + 1);   // consumed next iteration
@@ -344,6 +362,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __re
     }
   }
   __syncthreads();
+  if (tid == 0 && b_end < col_blocks) remv[b_end] |= ext;   // last block's contribution to the next chunk's first column
+  __syncthreads();
+  if (!final) {
+    for (int j = tid; j < col_blocks; j += SCAN_THREADS) {
+      remv_g[j] = remv[j];
+      keptw_g[j] = keptw[j];
+    }
+    return;
+  }
   // flag kept boxes by ORIGINAL index
   for (int i = tid; i < n; i += SCAN_THREADS)
     if ((keptw[i >> 6] >> (i & 63)) & 1ull) keep_flag[order[i]] = 1;
@@ -378,6 +405,8 @@ struct RnmsPlan {
   float* geom;
   u64* mask;
   unsigned char* keep_flag;
+  u64* remv_g;
+  u64* keptw_g;
   void* cub_temp;
   size_t total;
 };
@@ -411,6 +440,8 @@ static void plan_rnms(int n, void* ws, RnmsPlan* p) {
   p->geom = c.take<float>((size_t)kGeomFields * p->n_pad);
   p->mask = c.take<u64>((size_t)n * p->col_blocks);
   p->keep_flag = c.take<unsigned char>(n);
+  p->remv_g = c.take<u64>(2 * (size_t)p->col_blocks);
+  p->keptw_g = p->remv_g + p->col_blocks;
   p->cub_temp = c.take<unsigned char>(p->cub_bytes);
   p->total = align_up(c.off, 256);
 }
@@ -426,8 +457,20 @@ extern "C" size_t ryolo_rnms_workspace_bytes(int n) {
   return p.total;
 }
 
+static int rnms_impl(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep, void* workspace,
+                     size_t workspace_bytes, void* stream_, bool full_mask);
+
 extern "C" int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep, void* workspace,
                           size_t workspace_bytes, void* stream_) {
+  return rnms_impl(dets, n, thr, keep_out, num_keep, workspace, workspace_bytes, stream_, false);
+}
+extern "C" int ryolo_rnms_full_mask(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep,
+                                    void* workspace, size_t workspace_bytes, void* stream_) {
+  return rnms_impl(dets, n, thr, keep_out, num_keep, workspace, workspace_bytes, stream_, true);
+}
+
+static int rnms_impl(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep, void* workspace,
+                     size_t workspace_bytes, void* stream_, bool full_mask) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(n >= 0);
   RYOLO_ARG_CHECK(num_keep != nullptr);
@@ -467,12 +510,6 @@ extern "C" int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out
                                           (int)sizeof(MaskSmem)));
       attr_set = true;
     }
-    dim3 grid((p.col_blocks + CH - 1) / CH, p.col_blocks);
-    rnms_mask_kernel<<<grid, MASK_THREADS, sizeof(MaskSmem), stream>>>(p.geom, n, p.n_pad, p.col_blocks, thr,
-                                                                        thr >= 0.f ? 1 : 0, p.mask);
-    RYOLO_LAUNCH_CHECK();
-  }
-  {
     const size_t smem = (size_t)p.col_blocks * sizeof(u64) * 2;
     if (smem > 200 * 1024) {
       set_err("ryolo_rnms: n=%d too large for the single-CTA scan (col_blocks=%d)", n, p.col_blocks);
@@ -480,9 +517,22 @@ extern "C" int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out
     }
     if (smem > 40 * 1024)
       RYOLO_CUDA_TRY(cudaFuncSetAttribute(rnms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rnms_scan_kernel<<<1, SCAN_THREADS, smem, stream>>>(p.mask, n, p.col_blocks, p.order, p.keep_flag,
-                                                        reinterpret_cast<long long*>(keep_out), num_keep);
-    RYOLO_LAUNCH_CHECK();
+    RYOLO_CUDA_TRY(cudaMemsetAsync(p.remv_g, 0, 2 * (size_t)p.col_blocks * sizeof(u64), stream));
+    // Row chunks of `chunk` blocks: mask(chunk rows x all later columns, skipping what earlier chunks suppressed),
+    // then scan(chunk).  flags & 1 (full) computes every upper-triangle tile in one launch like the reference.
+    const int chunk = full_mask ? p.col_blocks : kRowChunkBlocks;
+    for (int b0 = 0; b0 < p.col_blocks; b0 += chunk) {
+      const int b1 = b0 + chunk < p.col_blocks ? b0 + chunk : p.col_blocks;
+      dim3 grid((p.col_blocks - b0 + CH - 1) / CH, b1 - b0);
+      rnms_mask_kernel<<<grid, MASK_THREADS, sizeof(MaskSmem), stream>>>(p.geom, n, p.n_pad, p.col_blocks, thr,
+                                                                          thr >= 0.f ? 1 : 0, p.mask, b0,
+                                                                          full_mask ? nullptr : p.remv_g);
+      RYOLO_LAUNCH_CHECK();
+      rnms_scan_kernel<<<1, SCAN_THREADS, smem, stream>>>(p.mask, n, p.col_blocks, p.order, p.keep_flag,
+                                                          reinterpret_cast<long long*>(keep_out), num_keep, b0, b1,
+                                                          p.remv_g, p.keptw_g, b1 == p.col_blocks ? 1 : 0);
+      RYOLO_LAUNCH_CHECK();
+    }
   }
   return RYOLO_OK;
 }

@@ -79,9 +79,9 @@ def rnms_debug(dets, threshold):
         ws = _workspace(ws_bytes, d.device)
         keep = torch.empty((n,), dtype=torch.long, device=d.device)
         num = torch.empty((1,), dtype=torch.int32, device=d.device)
-        st = _lib.lib.ryolo_rnms(_lib.ptr(d), n, float(threshold), _lib.ptr(keep), _lib.ptr(num), _lib.ptr(ws),
-                                 ws_bytes, _lib.stream_ptr(d.device))
-        _lib.check(st, "ryolo_rnms")
+        st = _lib.lib.ryolo_rnms_full_mask(_lib.ptr(d), n, float(threshold), _lib.ptr(keep), _lib.ptr(num), _lib.ptr(ws),
+                                           ws_bytes, _lib.stream_ptr(d.device))
+        _lib.check(st, "ryolo_rnms_full_mask")
         k = int(num.item())
         pb, po, pm = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         _lib.check(_lib.lib.ryolo_rnms_debug_views(_lib.ptr(ws), n, ctypes.byref(pb), ctypes.byref(po),

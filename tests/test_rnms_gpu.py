@@ -121,12 +121,25 @@ def test_wrapper_fixture():
     assert out.cpu().tolist() == [0, 3]   # utils/nms/nms_wrapper_test.py:35-43, analytic answer
 
 
-@pytest.mark.parametrize("n,canvas", [(2000, 250.0), (4000, 608.0)])
+@pytest.mark.parametrize("n,canvas", [(2000, 250.0), (4000, 608.0), (3000, 60.0)])
 def test_vs_cpu_oracle(n, canvas):
+    """r_nms (lazy chunked mask) vs the CPU oracle; the 60-px canvas is a dense set where most boxes are suppressed early"""
     dets = gen_dets(n, 77 + n, canvas)
     got = _ours(dets, 0.5).cpu().numpy()
     assert np.array_equal(got, orc_rnms(dets.numpy(), 0.5, variant=1))
     assert np.array_equal(got, orc_rnms(dets.numpy(), 0.5, variant=0))
+
+
+@pytest.mark.parametrize("n,canvas,thr", [(5000, 100.0, 0.3), (20000, 300.0, 0.5), (2500, 608.0, 0.1)])
+def test_lazy_chunked_equals_full_mask_and_reference(n, canvas, thr):
+    """the production path skips rows/columns suppressed by earlier 1024-box chunks; the kept list must not change"""
+    import rotate_yolov3_b200 as pkg
+    dets = gen_dets(n, 31 + n, canvas)
+    lazy = _ours(dets, thr).cpu().numpy()
+    full = pkg.nms.rnms_debug(dets.cuda(), thr)[0].cpu().numpy()
+    assert np.array_equal(lazy, full)
+    if ref_lib("cuda") is not None:
+        assert np.array_equal(lazy, _ref_cuda_keep(dets.numpy(), thr))
 
 
 def test_reference_boundary_behaviour():
