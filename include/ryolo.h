@@ -155,7 +155,9 @@ typedef struct ryolo_conv_desc {
   int32_t cout;        /* filters                                                             */
   int32_t cout_stride; /* channel stride of the bf16 output buffer (>= round_up(cout, 32); channels
                           [cout, round_up(cout,32)) are written as zeros, nothing beyond)     */
-  int32_t ksize;       /* 1 or 3 (pad = (k-1)/2 as in models.py:53)                           */
+  int32_t ksize;       /* 1 or 3 (pad = (k-1)/2 as in models.py:53); 2 = 2x2 taps at offsets
+                          {-1,0}^2 and -2 = offsets {0,+1}^2 (the space-to-depth form of a
+                          3x3/stride-2 conv and its adjoint, see ryolo_space_to_depth)         */
   int32_t stride;      /* 1 or 2                                                              */
   int32_t has_act;     /* 1: PReLU with scalar `slope` (cfg activation=leaky), 0: linear      */
   float slope;         /* PReLU weight (nn.PReLU(num_parameters=1), models.py:65)             */
@@ -226,6 +228,15 @@ int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, void* z_dz,
  * pre-zeroed dst (dst_h x dst_w). */
 int ryolo_zero_insert2x(const void* src, int src_cstride, int batch, int h, int w, int c, void* dst,
                         int dst_cstride, int dst_h, int dst_w, void* stream);
+/* Space-to-depth of a padded-NHWC tensor with even H, W:
+ * xs[b, Y, X, (py*2+px)*C + c] = x[b, 2Y+py, 2X+px, c]  ([B, H/2+2, W/2+2, >=4C]).  A 3x3/stride-2/pad-1
+ * conv on x equals a ksize=2 (offsets -1..0), stride-1 conv on xs with the weight blocks
+ * W2[(qy,qx)][co][(py,px,c)] = W[co][c][kh][kw], kh = {(0,1):0,(1,0):1,(1,1):2}[(qy,py)] (zero for
+ * (0,0)), same for kw.  ryolo_depth_to_space is the adjoint (optionally accumulating). */
+int ryolo_space_to_depth(const void* x, int x_cstride, int batch, int h, int w, int c, void* xs,
+                         int xs_cstride, void* stream);
+int ryolo_depth_to_space(const void* dxs, int dxs_cstride, int batch, int h, int w, int c, void* gx,
+                         int gx_cstride, int accumulate, void* stream);
 /* fp32 NCHW [B,C,H,W] -> bf16 padded NHWC interior, channels [0,C) (head gradients). */
 int ryolo_nchw_to_padded(const float* src, int batch, int c, int h, int w, void* dst,
                          int dst_cstride, void* stream);

@@ -59,6 +59,8 @@ SIGNATURES = {
     "ryolo_bn_act_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _vp, _i, _i, _vp]),
     "ryolo_bn_act_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _i, _vp]),
     "ryolo_zero_insert2x": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "ryolo_space_to_depth": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "ryolo_depth_to_space": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "ryolo_nchw_to_padded": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "ryolo_im2col_first": (_i, [_vp, _i, _i, _i, _vp, _vp]),
 }

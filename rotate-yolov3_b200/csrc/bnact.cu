@@ -318,6 +318,37 @@ __global__ void __launch_bounds__(256) zero_insert2x_kernel(const __nv_bfloat16*
   *reinterpret_cast<uint4*>(dst + pad_off(b, 2 * y, 2 * x, ih, iw, dcs) + cg * 8) = v;
 }
 
+// space-to-depth for the stride-2 convolutions: xs[b, Y, X, (py*2+px)*C + c] = x[b, 2Y+py, 2X+px, c] (interior coordinates,
+// H and W even).  On xs a 3x3/stride-2/pad-1 conv is a 2x2-tap stride-1 conv (tap offsets -1..0) with 4C input channels
+// (7 of the 16 (tap, phase) weight blocks are zero) -- the same flat implicit GEMM, 1.78x instead of 4x MMA work.
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, int xcs, Geo g /*of x*/,
+                                                             __nv_bfloat16* __restrict__ xs, int scs) {
+  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int b, y, xx, cg;
+  if (!decode_item(g, item, b, y, xx, cg)) return;
+  const uint4 v = *reinterpret_cast<const uint4*>(x + pad_off(b, y, xx, g.h, g.w, xcs) + cg * 8);
+  const int ph = (y & 1) * 2 + (xx & 1);
+  *reinterpret_cast<uint4*>(xs + pad_off(b, y >> 1, xx >> 1, g.h >> 1, g.w >> 1, scs) + ph * g.c + cg * 8) = v;
+}
+// adjoint: gx[b, 2Y+py, 2X+px, c] (+)= dxs[b, Y, X, (py*2+px)*C + c]
+__global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16* __restrict__ dxs, int scs, Geo g /*of gx*/,
+                                                             __nv_bfloat16* __restrict__ gx, int gcs, int accumulate) {
+  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int b, y, xx, cg;
+  if (!decode_item(g, item, b, y, xx, cg)) return;
+  const int ph = (y & 1) * 2 + (xx & 1);
+  float d[8];
+  unpack8(*reinterpret_cast<const uint4*>(dxs + pad_off(b, y >> 1, xx >> 1, g.h >> 1, g.w >> 1, scs) + ph * g.c + cg * 8), d);
+  __nv_bfloat16* gp = gx + pad_off(b, y, xx, g.h, g.w, gcs) + cg * 8;
+  if (accumulate) {
+    float o[8];
+    unpack8(*reinterpret_cast<const uint4*>(gp), o);
+#pragma unroll
+    for (int e = 0; e < 8; e++) d[e] += o[e];
+  }
+  *reinterpret_cast<uint4*>(gp) = pack8(d);
+}
+
 // fp32 NCHW [B, C, H, W] -> bf16 padded NHWC (interior, channels [0, C)); one thread per (pixel, channel)
 __global__ void __launch_bounds__(256) nchw_to_padded_kernel(const float* __restrict__ src, int batch, int c, int h, int w,
                                                              __nv_bfloat16* __restrict__ dst, int dcs) {
@@ -465,6 +496,35 @@ extern "C" int ryolo_zero_insert2x(const void* src, int src_cstride, int batch, 
   zero_insert2x_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src),
                                                                            src_cstride, g, static_cast<__nv_bfloat16*>(dst),
                                                                            dst_cstride, dst_h, dst_w);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_space_to_depth(const void* x, int x_cstride, int batch, int h, int w, int c, void* xs, int xs_cstride,
+                                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(x && xs);
+  GEO_CHECK();
+  RYOLO_ARG_CHECK(h % 2 == 0 && w % 2 == 0 && xs_cstride >= 4 * c);
+  const Geo g = mk_geo(batch, h, w, c);
+  const size_t items = n_items(g);
+  space_to_depth_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_cstride,
+                                                                            g, static_cast<__nv_bfloat16*>(xs), xs_cstride);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_depth_to_space(const void* dxs, int dxs_cstride, int batch, int h, int w, int c, void* gx,
+                                    int gx_cstride, int accumulate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(dxs && gx);
+  GEO_CHECK();
+  RYOLO_ARG_CHECK(h % 2 == 0 && w % 2 == 0 && dxs_cstride >= 4 * c);
+  const Geo g = mk_geo(batch, h, w, c);
+  const size_t items = n_items(g);
+  depth_to_space_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dxs),
+                                                                            dxs_cstride, g, static_cast<__nv_bfloat16*>(gx),
+                                                                            gx_cstride, accumulate);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }

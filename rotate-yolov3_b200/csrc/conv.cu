@@ -40,7 +40,8 @@ constexpr int CONV_THREADS = 256;
 struct ConvParams {
   int np;             // B * (H+2) * (W+2): GEMM M
   int hp, wp;         // padded input height / width
-  int taps;           // 1 or 9
+  int taps;           // 1, 9 (3x3, offsets -1..1) or 4 (2x2, offsets -1..0, or 0..1 when tap_flip)
+  int tap_flip;
   int kchunks;        // cin_pad / 64
   int cout;           // real filters
   int cout_pad;       // rows per tap in the packed weight
@@ -124,6 +125,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int tap = kk / p.kchunks, kc = kk % p.kchunks;
           int off = 0;
           if (p.taps == 9) off = (tap / 3 - 1) * p.wp + (tap % 3 - 1);
+          else if (p.taps == 4) off = (tap / 2 - 1 + p.tap_flip) * p.wp + (tap % 2 - 1 + p.tap_flip);
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * S::kStageBytes;
           mbar_expect_tx(full_bar(stage), S::kStageBytes);
@@ -352,7 +354,8 @@ static ConvGeom conv_geom(const ryolo_conv_desc* d) {
   g.cin_pad = round_up(d->cin, 64);
   g.bn = d->cout > 128 ? 256 : (d->cout > 64 ? 128 : 64);
   g.cout_pad = round_up(d->cout, g.bn);
-  g.taps = d->ksize * d->ksize;
+  const int k = d->ksize < 0 ? -d->ksize : d->ksize;
+  g.taps = k * k;
   return g;
 }
 
@@ -433,11 +436,12 @@ extern "C" int ryolo_conv_pack_weights(const ryolo_conv_desc* d, const float* we
                                        void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(d && weight && packed_out);
-  RYOLO_ARG_CHECK(d->ksize == 1 || d->ksize == 3);
+  RYOLO_ARG_CHECK(d->ksize == 1 || d->ksize == 3 || d->ksize == 2 || d->ksize == -2);
   const ConvGeom g = conv_geom(d);
   const size_t total = (size_t)g.taps * g.cout_pad * g.cin_pad;
   const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-  conv_pack_weights_kernel<<<blocks, 256, 0, stream>>>(weight, scale, d->cout, d->cin, d->ksize, g.cout_pad, g.cin_pad,
+  conv_pack_weights_kernel<<<blocks, 256, 0, stream>>>(weight, scale, d->cout, d->cin, d->ksize < 0 ? -d->ksize : d->ksize,
+                                                        g.cout_pad, g.cin_pad,
                                                         static_cast<__nv_bfloat16*>(packed_out));
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
@@ -456,8 +460,8 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(d && x && packed_w && bias && y);
   RYOLO_ARG_CHECK(d->batch > 0 && d->in_h > 0 && d->in_w > 0 && d->cin > 0 && d->cout > 0);
-  RYOLO_ARG_CHECK(d->ksize == 1 || d->ksize == 3);
-  RYOLO_ARG_CHECK(d->stride == 1 || d->stride == 2);
+  RYOLO_ARG_CHECK(d->ksize == 1 || d->ksize == 3 || d->ksize == 2 || d->ksize == -2);
+  RYOLO_ARG_CHECK(d->stride == 1 || (d->stride == 2 && d->ksize != 2 && d->ksize != -2));
   RYOLO_ARG_CHECK(!(d->stride == 2 && d->upsample2x));
   RYOLO_ARG_CHECK(!d->has_residual || (residual != nullptr && d->stride == 1 && !d->upsample2x &&
                                         d->res_stride % 8 == 0 && d->out_dtype == RYOLO_DT_BF16));
@@ -474,6 +478,7 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   RYOLO_ARG_CHECK(np < (1ll << 31) - 4096);
   p.np = (int)np;
   p.taps = g.taps;
+  p.tap_flip = d->ksize == -2 ? 1 : 0;
   p.kchunks = g.cin_pad / 64;
   p.cout = d->cout;
   p.cout_pad = g.cout_pad;

@@ -50,6 +50,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_const
   const int k_iters = k_end - k_begin;
   int off = 0;
   if (p.taps == 9) off = (tap / 3 - 1) * p.wp + (tap % 3 - 1);
+  else if (p.taps == 4) off = (tap / 2 - 1) * p.wp + (tap % 2 - 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; s++) {
@@ -159,7 +160,7 @@ extern "C" int ryolo_conv_wgrad(const void* dz, int dz_cstride, int cout_pad, co
                                 int batch, int in_h, int in_w, int ksize, float* dw, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(dz && x && dw && batch > 0 && in_h > 0 && in_w > 0);
-  RYOLO_ARG_CHECK(ksize == 1 || ksize == 3);
+  RYOLO_ARG_CHECK(ksize == 1 || ksize == 3 || ksize == 2);
   RYOLO_ARG_CHECK(cout_pad > 0 && cout_pad % 64 == 0 && cin_pad > 0 && cin_pad % 64 == 0);
   RYOLO_ARG_CHECK(dz_cstride >= cout_pad && dz_cstride % 8 == 0 && x_cstride >= cin_pad && x_cstride % 8 == 0);
   WgradParams p;

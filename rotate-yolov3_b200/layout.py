@@ -55,6 +55,31 @@ def padded_bias(desc, bias):
     return b
 
 
+_S2D_K = {(0, 1): 0, (1, 0): 1, (1, 1): 2}   # (tap q, phase p) -> original kernel index; (0, 0) has no contribution
+
+
+def s2d_weight(w):
+    """[cout, C, 3, 3] weights of a 3x3/stride-2/pad-1 conv -> [cout, 4C, 2, 2] weights of the equivalent 2x2-tap
+    stride-1 conv on the space-to-depth input (channel = (py*2+px)*C + c, tap (qy, qx) at offset (qy-1, qx-1))."""
+    cout, c = w.shape[0], w.shape[1]
+    w2 = torch.zeros((cout, 4, c, 2, 2), dtype=w.dtype, device=w.device)
+    for (qy, py), kh in _S2D_K.items():
+        for (qx, px), kw in _S2D_K.items():
+            w2[:, py * 2 + px, :, qy, qx] = w[:, :, kh, kw]
+    return w2.reshape(cout, 4 * c, 2, 2)
+
+
+def s2d_weight_grad(dw2, c):
+    """inverse gather of s2d_weight for gradients: [cout, 4C, 2, 2] -> [cout, C, 3, 3]"""
+    cout = dw2.shape[0]
+    d = dw2.reshape(cout, 4, c, 2, 2)
+    dw = torch.zeros((cout, c, 3, 3), dtype=dw2.dtype, device=dw2.device)
+    for (qy, py), kh in _S2D_K.items():
+        for (qx, px), kw in _S2D_K.items():
+            dw[:, :, kh, kw] = d[:, py * 2 + px, :, qy, qx]
+    return dw
+
+
 def conv_fwd(desc, x_ptr, packed_w, bias, y_ptr, residual_ptr=None, device=None):
     st = _lib.lib.ryolo_conv_bn_act_fwd(ctypes.byref(desc), ctypes.c_void_p(x_ptr), _lib.ptr(packed_w), _lib.ptr(bias),
                                         ctypes.c_void_p(residual_ptr) if residual_ptr else None,

@@ -279,10 +279,22 @@ class Darknet(nn.Module):
                 fuse_up = nxt == "upsample" and i not in self.routes and int(defs[i + 1]["stride"]) == 2
                 is_head = nxt == "yolo"
                 mat = i + 1 if (fuse_res or fuse_up) else i       # the layer index whose output is materialised
-                desc = L.make_desc(batch, src.h, src.w, src.c, src.cs, cout, 0, k, s, slope is not None,
-                                   slope if slope is not None else 0.0, fuse_res, 0, fuse_up, is_head)
                 if src.c != wt.shape[1]:
                     raise RuntimeError("channel mismatch at block %d" % i)
+                x_ptr = src.ptr
+                use_s2d = s == 2 and k == 3 and src.h % 2 == 0 and src.w % 2 == 0 and src.c % 8 == 0
+                if use_s2d:
+                    # 3x3/stride-2 as a 2x2-tap stride-1 conv on the space-to-depth copy of the input (1.78x instead of
+                    # 4x MMA work; also removes the 32->64 channel padding of the first down-sampling layer)
+                    xs = L.alloc_padded(batch, src.h // 2, src.w // 2, L.round_up(4 * src.c, 64), device)
+                    steps.append(("s2d", dict(x=src.ptr, xcs=src.cs, h=src.h, w=src.w, c=src.c, xs=xs, keep=src)))
+                    desc = L.make_desc(batch, src.h // 2, src.w // 2, 4 * src.c, xs.shape[-1], cout, 0, 2, 1,
+                                       slope is not None, slope if slope is not None else 0.0, fuse_res, 0, fuse_up, is_head)
+                    wt = L.s2d_weight(wt)
+                    x_ptr = xs.data_ptr()
+                else:
+                    desc = L.make_desc(batch, src.h, src.w, src.c, src.cs, cout, 0, k, s, slope is not None,
+                                       slope if slope is not None else 0.0, fuse_res, 0, fuse_up, is_head)
                 res = None
                 if is_head:
                     out = torch.empty((batch, cout, oh, ow), dtype=torch.float32, device=device)
@@ -302,7 +314,7 @@ class Darknet(nn.Module):
                         desc.res_stride = res.cs
                 pw = L.pack_weights(desc, wt, scale)
                 pb = L.padded_bias(desc, bias)
-                steps.append(("conv", dict(desc=desc, x=src.ptr, w=pw, b=pb, y=out_ptr,
+                steps.append(("conv", dict(desc=desc, x=x_ptr, w=pw, b=pb, y=out_ptr,
                                            r=res.ptr if res is not None else None,
                                            keep=(src, res, views[mat] if not is_head else out))))
                 i += 2 if (fuse_res or fuse_up) else 1
@@ -344,7 +356,11 @@ class Darknet(nn.Module):
             lib = _lib.lib
             stream = _lib.stream_ptr(x.device)
             for kind, a in plan["steps"]:
-                if kind == "first":
+                if kind == "s2d":
+                    st = lib.ryolo_space_to_depth(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"],
+                                                  _lib.ptr(a["xs"]), a["xs"].shape[-1], stream)
+                    _lib.check(st, "ryolo_space_to_depth")
+                elif kind == "first":
                     v = a["out"]
                     st = lib.ryolo_conv_first_fwd(_lib.ptr(x), b, h, w, _lib.ptr(a["w"]), _lib.ptr(a["b"]), a["cout"],
                                                   a["slope"], ctypes.c_void_p(v.ptr), v.cs, stream)

@@ -105,6 +105,7 @@ class TrainPlan:
                 else:
                     blk.src, blk.gsrc = views[i - 1], gviews[i - 1]
                     blk.k_eff = blk.k
+                blk.s2d = False
                 blk.fuse_res = nxt == "shortcut" and i not in model.routes
                 blk.fuse_up = nxt == "upsample" and i not in model.routes and int(defs[i + 1]["stride"]) == 2
                 blk.is_head = nxt == "yolo"
@@ -131,17 +132,32 @@ class TrainPlan:
                     blk.mean, blk.invstd, blk.scale, blk.shift = (torch.zeros(blk.cout, dtype=torch.float32, device=device)
                                                                   for _ in range(4))
                     blk.bsums = torch.zeros(2 * blk.cout + 1, dtype=torch.float32, device=device)
-                if blk.stride == 2:
-                    blk.dz_up = L.alloc_padded(batch, blk.src.h, blk.src.w, blk.cout_pad, device)  # zero-inserted dz
+                blk.s2d = (i > 0 and blk.stride == 2 and blk.k == 3 and blk.src.h % 2 == 0 and blk.src.w % 2 == 0
+                           and blk.src.c % 8 == 0)
+                if blk.s2d:
+                    # 3x3/stride-2 block on the space-to-depth copy of its input: 2x2 taps, 4C channels, stride 1
+                    blk.xs_cs = L.round_up(4 * blk.src.c, 64)
+                    blk.xs = L.alloc_padded(batch, blk.src.h // 2, blk.src.w // 2, blk.xs_cs, device)
+                    blk.dxs = L.alloc_padded(batch, blk.src.h // 2, blk.src.w // 2, blk.xs_cs, device)
+                    blk.k_eff = 2
+                    blk.cin_eff, blk.cin_pad = 4 * blk.src.c, blk.xs_cs
+                    blk.fdesc = L.make_desc(batch, blk.src.h // 2, blk.src.w // 2, blk.cin_eff, blk.xs_cs, blk.cout,
+                                            0 if blk.is_head else blk.cout_pad, 2, 1, False, 0.0, False, 0, False, blk.is_head)
+                    blk.ddesc = L.make_desc(batch, blk.src.h // 2, blk.src.w // 2, blk.cout, blk.cout_pad, blk.cin_eff,
+                                            blk.xs_cs, -2, 1, False, 0.0, False, 0, False, False)
+                else:
+                    blk.cin_eff = blk.cin
+                    if blk.stride == 2:
+                        blk.dz_up = L.alloc_padded(batch, blk.src.h, blk.src.w, blk.cout_pad, device)  # zero-inserted dz
+                    # forward descriptor: raw conv (no bias / activation); heads keep their bias and write fp32 NCHW
+                    blk.fdesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cin, blk.src.cs, blk.cout,
+                                            0 if blk.is_head else blk.cout_pad, blk.k_eff, blk.stride, False, 0.0, False, 0,
+                                            False, blk.is_head)
+                    if i > 0:
+                        # dgrad: stride-1 conv of dz (at the INPUT resolution) with mirrored taps / transposed weights
+                        blk.ddesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cout, blk.cout_pad, blk.cin, blk.gsrc.cs,
+                                                blk.k, 1, False, 0.0, False, blk.gsrc.cs, False, False)
                 blk.dw = torch.zeros((blk.k_eff * blk.k_eff, blk.cout_pad, blk.cin_pad), dtype=torch.float32, device=device)
-                # forward descriptor: raw conv (no bias / activation); heads keep their bias and write fp32 NCHW
-                blk.fdesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cin, blk.src.cs, blk.cout,
-                                        0 if blk.is_head else blk.cout_pad, blk.k_eff, blk.stride, False, 0.0, False, 0,
-                                        False, blk.is_head)
-                if i > 0:
-                    # dgrad: stride-1 conv of dz (at the INPUT resolution) with mirrored taps / transposed weights
-                    blk.ddesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cout, blk.cout_pad, blk.cin, blk.gsrc.cs,
-                                            blk.k, 1, False, 0.0, False, blk.gsrc.cs, False, False)
                 blocks.append(blk)
                 i += 2 if (blk.fuse_res or blk.fuse_up) else 1
                 continue
@@ -187,14 +203,20 @@ class TrainPlan:
             w = seq.Conv2d.weight.detach()
             if blk.i == 0:
                 w = w.reshape(blk.cout, 27, 1, 1)
+            x_ptr = blk.src.ptr
+            if blk.s2d:
+                _lib.check(lib.ryolo_space_to_depth(ctypes.c_void_p(blk.src.ptr), blk.src.cs, self.batch, blk.src.h, blk.src.w,
+                                                    blk.src.c, _lib.ptr(blk.xs), blk.xs_cs, st), "s2d")
+                w = L.s2d_weight(w)
+                x_ptr = blk.xs.data_ptr()
             blk.pw = L.pack_weights(blk.fdesc, w)
             if blk.is_head:
                 bias = L.padded_bias(blk.fdesc, seq.Conv2d.bias.detach())
-                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.fdesc), ctypes.c_void_p(blk.src.ptr), _lib.ptr(blk.pw),
+                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.fdesc), ctypes.c_void_p(x_ptr), _lib.ptr(blk.pw),
                                                      _lib.ptr(bias), None, _lib.ptr(blk.out), None, 0, st), "conv head")
                 heads.append(blk)
                 continue
-            _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.fdesc), ctypes.c_void_p(blk.src.ptr), _lib.ptr(blk.pw),
+            _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.fdesc), ctypes.c_void_p(x_ptr), _lib.ptr(blk.pw),
                                                  _lib.ptr(self.zero_bias), None, _lib.ptr(blk.z), None, 0, st), "conv")
             cnt = n_per_pixel * blk.oh * blk.ow
             if blk.has_bn:
@@ -256,15 +278,29 @@ class TrainPlan:
                 if blk.has_act:
                     pgrads[(blk.i, "activation.weight")] = blk.bsums[2 * blk.cout:]
                 dz = blk.z
+            blk.dw.zero_()
+            k = blk.k_eff
+            if blk.s2d:
+                _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.cout_pad, blk.cout_pad, _lib.ptr(blk.xs), blk.xs_cs,
+                                                blk.cin_pad, self.batch, blk.src.h // 2, blk.src.w // 2, 2, _lib.ptr(blk.dw),
+                                                st), "wgrad s2d")
+                gw2 = blk.dw.view(2, 2, blk.cout_pad, blk.cin_pad)[:, :, :blk.cout, :blk.cin_eff].permute(2, 3, 0, 1)
+                pgrads[(blk.i, "Conv2d.weight")] = L.s2d_weight_grad(gw2, blk.src.c)
+                w2 = L.s2d_weight(seq.Conv2d.weight.detach())
+                wd = w2.flip(2, 3).permute(1, 0, 2, 3).contiguous()      # [4C, cout, 2, 2], taps mirrored (offsets 0..+1)
+                pwd = L.pack_weights(blk.ddesc, wd)
+                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(pwd),
+                                                     _lib.ptr(self.zero_bias), None, _lib.ptr(blk.dxs), None, 0, st), "dgrad s2d")
+                _lib.check(lib.ryolo_depth_to_space(_lib.ptr(blk.dxs), blk.xs_cs, self.batch, blk.src.h, blk.src.w, blk.src.c,
+                                                    ctypes.c_void_p(blk.gsrc.ptr), blk.gsrc.cs, int(blk.gsrc_acc), st), "d2s")
+                continue
             if blk.stride == 2:
                 _lib.check(lib.ryolo_zero_insert2x(_lib.ptr(dz), blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout_pad,
                                                    _lib.ptr(blk.dz_up), blk.cout_pad, blk.src.h, blk.src.w, st), "zero_insert")
                 dz = blk.dz_up
-            blk.dw.zero_()
             _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.cout_pad, blk.cout_pad, ctypes.c_void_p(blk.src.ptr), blk.src.cs,
                                             blk.cin_pad, self.batch, blk.src.h, blk.src.w, blk.k_eff, _lib.ptr(blk.dw), st),
                        "wgrad")
-            k = blk.k_eff
             gw = blk.dw.view(k, k, blk.cout_pad, blk.cin_pad)[:, :, :blk.cout, :blk.cin].permute(2, 3, 0, 1)
             pgrads[(blk.i, "Conv2d.weight")] = gw.reshape(seq.Conv2d.weight.shape).clone()
             if blk.i > 0:

@@ -149,3 +149,41 @@ def test_conv_wgrad_vs_torch(cfg):
     scale = float(want.abs().max())
     assert float((got - want).abs().max()) <= 2e-3 * scale, (float((got - want).abs().max()), scale)
     assert float(dw.view(k, k, cout_pad, cin_pad)[:, :, cout:].abs().max() if cout_pad > cout else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(32, 64, 16, 20), (64, 128, 38, 38), (256, 512, 12, 10)])
+def test_stride2_via_space_to_depth_vs_torch(cin, cout, h, w):
+    """3x3/stride-2/pad-1 conv = space-to-depth + 2x2-tap stride-1 implicit GEMM (ksize = 2) with remapped weights"""
+    import rotate_yolov3_b200 as pkg
+    from rotate_yolov3_b200 import layout as L
+    lib = pkg._lib.lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(cin)
+    b = 2
+    x = torch.randn(b, cin, h, w, generator=g).to(dev).to(torch.bfloat16).float()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev).to(torch.bfloat16).float()
+    bias = torch.randn(cout, generator=g).to(dev)
+    xb = L.to_padded_nhwc(x, L.round_up(cin, 64))
+    xs = L.alloc_padded(b, h // 2, w // 2, L.round_up(4 * cin, 64), dev)
+    assert lib.ryolo_space_to_depth(pkg._lib.ptr(xb), xb.shape[-1], b, h, w, cin, pkg._lib.ptr(xs), xs.shape[-1],
+                                    pkg._lib.stream_ptr(dev)) == 0
+    bn = 256 if cout > 128 else (128 if cout > 64 else 64)
+    cout_pad = L.round_up(cout, bn)
+    desc = L.make_desc(b, h // 2, w // 2, 4 * cin, xs.shape[-1], cout, cout_pad, 2, 1, True, 0.1)
+    pw = L.pack_weights(desc, L.s2d_weight(wt))
+    pb = L.padded_bias(desc, bias)
+    y = L.alloc_padded(b, h // 2, w // 2, cout_pad, dev)
+    L.conv_fwd(desc, xs.data_ptr(), pw, pb, y.data_ptr(), None, dev)
+    torch.cuda.synchronize()
+    want = _ref(x, wt, bias, 2, 0.1, True)
+    got = L.from_padded_nhwc(y, cout)
+    err = (got - want).abs()
+    assert bool((err <= 2.0 ** -8 * want.abs() + 1e-3 * float(want.abs().max()) * 2.0 ** -8 + 1e-6).all()), float(err.max())
+    # adjoint pair: depth_to_space(space_to_depth(x)) == x, accumulate doubles it
+    back = L.alloc_padded(b, h, w, xb.shape[-1], dev)
+    assert lib.ryolo_depth_to_space(pkg._lib.ptr(xs), xs.shape[-1], b, h, w, cin, pkg._lib.ptr(back), back.shape[-1], 0,
+                                    pkg._lib.stream_ptr(dev)) == 0
+    assert torch.equal(L.from_padded_nhwc(back, cin), x)
+    assert lib.ryolo_depth_to_space(pkg._lib.ptr(xs), xs.shape[-1], b, h, w, cin, pkg._lib.ptr(back), back.shape[-1], 1,
+                                    pkg._lib.stream_ptr(dev)) == 0
+    assert torch.allclose(L.from_padded_nhwc(back, cin), 2 * x, rtol=1e-2, atol=1e-2)
