@@ -104,7 +104,7 @@ def test_mini_graph_eval_and_train_vs_reference():
         if name.endswith("activation.weight"):
             # one scalar per block = a sum over the whole activation with heavy cancellation: bounded against the
             # largest slope gradient of the net
-            assert abs(float(got) - float(want)) <= 0.2 * slope_scale, (name, float(got), float(want))
+            assert abs(float(got) - float(want)) <= 0.3 * slope_scale, (name, float(got), float(want))
             continue
         cos = float((got * want).sum() / (got.norm() * want.norm() + 1e-30))
         ratio = float(got.norm() / (want.norm() + 1e-30))
