@@ -175,6 +175,17 @@ typedef struct ryolo_conv_desc {
 size_t ryolo_conv_packed_weight_bytes(const ryolo_conv_desc* d);
 int ryolo_conv_pack_weights(const ryolo_conv_desc* d, const float* weight, const float* scale,
                             void* packed_out, void* stream);
+/* Same with the operand transform done in the packing kernel (no framework-side flips / transposes / gathers):
+ * mode 0 = plain; 1 = dgrad operand of a plain conv (`weight` is the FORWARD weight, `d` the dgrad
+ * descriptor: taps mirrored, matrix transposed); 2 = space-to-depth form of a 3x3/stride-2 conv
+ * (`weight` [cout, C, 3, 3], d->cin = 4C, d->ksize = 2); 3 = dgrad operand of mode 2 (d->cout = 4C,
+ * d->ksize = -2).  ryolo_conv_unpack_wgrad is the inverse gather for weight GRADIENTS: wgrad output
+ * [taps][cout_pad][cin_pad] -> nn.Conv2d layout [cout][cin][k][k] (mode 0) or, from the
+ * space-to-depth form, [cout][C][3][3] (mode 2, cin = C). */
+int ryolo_conv_pack_weights_ex(const ryolo_conv_desc* d, const float* weight, const float* scale,
+                               void* packed_out, int mode, void* stream);
+int ryolo_conv_unpack_wgrad(const float* dw, int cout_pad, int cin_pad, int mode, int cout, int cin,
+                            int ksize, float* grad, void* stream);
 /* y = act(conv(x, W') + bias) [+ residual].  bias: fp32 [cout_pad] (zero beyond cout). */
 size_t ryolo_conv_workspace_bytes(const ryolo_conv_desc* d);
 int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, const void* packed_w,

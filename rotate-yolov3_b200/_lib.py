@@ -50,6 +50,8 @@ SIGNATURES = {
     "ryolo_yolo_decode": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _f, _f, _i, _vp, _i, _i, _vp, _vp]),
     "ryolo_conv_packed_weight_bytes": (_sz, [ctypes.POINTER(ConvDesc)]),
     "ryolo_conv_pack_weights": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "ryolo_conv_pack_weights_ex": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _i, _vp]),
+    "ryolo_conv_unpack_wgrad": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ryolo_conv_workspace_bytes": (_sz, [ctypes.POINTER(ConvDesc)]),
     "ryolo_conv_bn_act_fwd": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ryolo_conv_first_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _f, _vp, _i, _vp]),

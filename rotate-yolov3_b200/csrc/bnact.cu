@@ -349,17 +349,29 @@ __global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16
   *reinterpret_cast<uint4*>(gp) = pack8(d);
 }
 
-// fp32 NCHW [B, C, H, W] -> bf16 padded NHWC (interior, channels [0, C)); one thread per (pixel, channel)
+// fp32 NCHW [B, C, H, W] -> bf16 padded NHWC (interior, channels [0, C)).  Thread = (pixel x, 8-channel group):
+// consecutive threads read consecutive x of the same channel plane (coalesced) and write 16 bytes each.
 __global__ void __launch_bounds__(256) nchw_to_padded_kernel(const float* __restrict__ src, int batch, int c, int h, int w,
                                                              __nv_bfloat16* __restrict__ dst, int dcs) {
+  const int cgs = (c + 7) >> 3;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)batch * c * h * w;
+  const size_t total = (size_t)batch * cgs * h * w;
   if (i >= total) return;
   const int x = (int)(i % w);
   const int y = (int)((i / w) % h);
-  const int ch = (int)((i / ((size_t)w * h)) % c);
-  const int b = (int)(i / ((size_t)w * h * c));
-  dst[pad_off(b, y, x, h, w, dcs) + ch] = __float2bfloat16_rn(src[i]);
+  const int cg = (int)((i / ((size_t)w * h)) % cgs);
+  const int b = (int)(i / ((size_t)w * h * cgs));
+  const size_t plane = (size_t)h * w;
+  const float* s = src + ((size_t)b * c + cg * 8) * plane + (size_t)y * w + x;
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) f[e] = (cg * 8 + e < c) ? __ldg(s + e * plane) : 0.f;
+  __nv_bfloat16* o = dst + pad_off(b, y, x, h, w, dcs) + cg * 8;
+  if (cg * 8 + 8 <= dcs) {
+    *reinterpret_cast<uint4*>(o) = pack8(f);
+  } else {
+    for (int e = 0; e < 8 && cg * 8 + e < dcs; e++) o[e] = __float2bfloat16_rn(f[e]);
+  }
 }
 
 // im2col of the 3-channel image for the first 3x3/stride-1/pad-1 conv: column index = c*9 + kh*3 + kw (the flattening
@@ -533,7 +545,8 @@ extern "C" int ryolo_nchw_to_padded(const float* src, int batch, int c, int h, i
                                     void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(src && dst && batch > 0 && c > 0 && h > 0 && w > 0 && dst_cstride >= c);
-  const size_t total = (size_t)batch * c * h * w;
+  RYOLO_ARG_CHECK(dst_cstride % 8 == 0);
+  const size_t total = (size_t)batch * ((c + 7) / 8) * h * w;
   nchw_to_padded_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, batch, c, h, w,
                                                                             static_cast<__nv_bfloat16*>(dst), dst_cstride);
   RYOLO_LAUNCH_CHECK();

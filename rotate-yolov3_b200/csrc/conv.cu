@@ -277,8 +277,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: [cout, cin, k, k] fp32 (* per-filter scale) -> bf16 [k*k][cout_pad][cin_pad], zero padded
 // ---------------------------------------------------------------------------------------------------------------
+// mode 0: plain            packed[tap][co][ci] = w[co][ci][kh][kw] (* scale[co])
+// mode 1: dgrad of mode 0  packed[tap][co][ci] = w[ci][co][k-1-kh][k-1-kw]      (w = the FORWARD weight [cin_d, cout_d, k, k])
+// mode 2: space-to-depth   packed[(qy,qx)][co][(py*2+px)*C + c] = w[co][c][kh(qy,py)][kw(qx,px)] or 0   (w = [cout, C, 3, 3])
+// mode 3: dgrad of mode 2  packed[(ty,tx)][(py*2+px)*C + c][ci] = w[ci][c][kh(1-ty,py)][kw(1-tx,px)] or 0
+__device__ __forceinline__ int s2d_k(int q, int p) { return q == 0 ? (p == 1 ? 0 : -1) : (p == 0 ? 1 : 2); }
+
 __global__ void conv_pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ scale, int cout, int cin,
-                                         int ks, int cout_pad, int cin_pad, __nv_bfloat16* __restrict__ out) {
+                                         int ks, int cout_pad, int cin_pad, int mode, __nv_bfloat16* __restrict__ out) {
   const size_t total = (size_t)ks * ks * cout_pad * cin_pad;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % cin_pad);
@@ -286,10 +292,41 @@ __global__ void conv_pack_weights_kernel(const float* __restrict__ w, const floa
     const int tap = (int)(i / ((size_t)cin_pad * cout_pad));
     float v = 0.f;
     if (ci < cin && co < cout) {
-      v = w[(((size_t)co * cin + ci) * ks + tap / ks) * ks + tap % ks];
-      if (scale) v *= scale[co];
+      const int ty = tap / ks, tx = tap % ks;
+      if (mode == 0) {
+        v = w[(((size_t)co * cin + ci) * ks + ty) * ks + tx];
+      } else if (mode == 1) {
+        v = w[(((size_t)ci * cout + co) * ks + (ks - 1 - ty)) * ks + (ks - 1 - tx)];
+      } else if (mode == 2) {
+        const int C = cin >> 2, ph = ci / C, c = ci - ph * C;
+        const int kh = s2d_k(ty, ph >> 1), kw = s2d_k(tx, ph & 1);
+        if (kh >= 0 && kw >= 0) v = w[(((size_t)co * C + c) * 3 + kh) * 3 + kw];
+      } else {
+        const int C = cout >> 2, ph = co / C, c = co - ph * C;
+        const int kh = s2d_k(1 - ty, ph >> 1), kw = s2d_k(1 - tx, ph & 1);
+        if (kh >= 0 && kw >= 0) v = w[(((size_t)ci * C + c) * 3 + kh) * 3 + kw];
+      }
+      if (scale && (mode == 0 || mode == 2)) v *= scale[co];
     }
     out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// weight-gradient unpack: dw fp32 [taps][cout_pad][cin_pad] (wgrad output) -> grad [cout][cin][k][k] in nn.Conv2d layout.
+// mode 0: plain k x k;  mode 2: space-to-depth form (taps 2x2, cin_eff = 4C) -> [cout][C][3][3]
+__global__ void conv_unpack_wgrad_kernel(const float* __restrict__ dw, int cout_pad, int cin_pad, int mode, int cout, int cin,
+                                         int ks, float* __restrict__ grad) {
+  const size_t total = (size_t)cout * cin * ks * ks;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kw = (int)(i % ks), kh = (int)((i / ks) % ks);
+  const int c = (int)((i / ((size_t)ks * ks)) % cin);
+  const int co = (int)(i / ((size_t)ks * ks * cin));
+  if (mode == 0) {
+    grad[i] = dw[((size_t)(kh * ks + kw) * cout_pad + co) * cin_pad + c];
+  } else {
+    const int qy = kh == 0 ? 0 : 1, py = kh == 1 ? 0 : 1, qx = kw == 0 ? 0 : 1, px = kw == 1 ? 0 : 1;
+    grad[i] = dw[((size_t)(qy * 2 + qx) * cout_pad + co) * cin_pad + (py * 2 + px) * cin + c];
   }
 }
 
@@ -432,16 +469,37 @@ extern "C" size_t ryolo_conv_packed_weight_bytes(const ryolo_conv_desc* d) {
   return (size_t)g.taps * g.cout_pad * g.cin_pad * 2;
 }
 
+extern "C" int ryolo_conv_pack_weights_ex(const ryolo_conv_desc* d, const float* weight, const float* scale,
+                                          void* packed_out, int mode, void* stream_);
+
 extern "C" int ryolo_conv_pack_weights(const ryolo_conv_desc* d, const float* weight, const float* scale, void* packed_out,
                                        void* stream_) {
+  return ryolo_conv_pack_weights_ex(d, weight, scale, packed_out, 0, stream_);
+}
+
+extern "C" int ryolo_conv_unpack_wgrad(const float* dw, int cout_pad, int cin_pad, int mode, int cout, int cin, int ksize,
+                                       float* grad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  RYOLO_ARG_CHECK(d && weight && packed_out);
+  RYOLO_ARG_CHECK(dw && grad && cout > 0 && cin > 0 && (mode == 0 || mode == 2));
+  RYOLO_ARG_CHECK(mode == 0 ? (ksize == 1 || ksize == 3) : ksize == 3);
+  const size_t total = (size_t)cout * cin * ksize * ksize;
+  conv_unpack_wgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dw, cout_pad, cin_pad, mode, cout, cin, ksize,
+                                                                                grad);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_conv_pack_weights_ex(const ryolo_conv_desc* d, const float* weight, const float* scale,
+                                          void* packed_out, int mode, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(d && weight && packed_out && mode >= 0 && mode <= 3);
+  RYOLO_ARG_CHECK(mode < 2 || ((d->ksize == 2 || d->ksize == -2) && (mode == 2 ? d->cin % 4 == 0 : d->cout % 4 == 0)));
   RYOLO_ARG_CHECK(d->ksize == 1 || d->ksize == 3 || d->ksize == 2 || d->ksize == -2);
   const ConvGeom g = conv_geom(d);
   const size_t total = (size_t)g.taps * g.cout_pad * g.cin_pad;
   const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   conv_pack_weights_kernel<<<blocks, 256, 0, stream>>>(weight, scale, d->cout, d->cin, d->ksize < 0 ? -d->ksize : d->ksize,
-                                                        g.cout_pad, g.cin_pad,
+                                                        g.cout_pad, g.cin_pad, mode,
                                                         static_cast<__nv_bfloat16*>(packed_out));
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;

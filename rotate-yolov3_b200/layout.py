@@ -36,15 +36,20 @@ def make_desc(batch, in_h, in_w, cin, cin_stride, cout, cout_stride, ksize, stri
                          _lib.DT_F32 if out_f32 else _lib.DT_BF16)
 
 
-def pack_weights(desc, weight, scale=None):
-    """weight [cout, cin, k, k] fp32 CUDA (+ optional per-filter scale) -> packed bf16 GEMM operand (uint8 tensor)."""
-    nbytes = _lib.lib.ryolo_conv_packed_weight_bytes(ctypes.byref(desc))
-    out = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
-    w = weight.detach().float().contiguous()
+def pack_weights(desc, weight, scale=None, mode=0, out=None):
+    """fp32 CUDA conv weight (+ optional per-filter scale) -> packed bf16 GEMM operand (uint8 tensor).  mode: see
+    ryolo_conv_pack_weights_ex (0 plain, 1 dgrad of plain, 2 space-to-depth, 3 dgrad of space-to-depth); for modes
+    1-3 `weight` is the ORIGINAL nn.Conv2d weight and the transform happens inside the packing kernel."""
+    if out is None:
+        nbytes = _lib.lib.ryolo_conv_packed_weight_bytes(ctypes.byref(desc))
+        out = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
     s = scale.detach().float().contiguous() if scale is not None else None
-    st = _lib.lib.ryolo_conv_pack_weights(ctypes.byref(desc), _lib.ptr(w), _lib.ptr(s) if s is not None else None,
-                                          _lib.ptr(out), _lib.stream_ptr(weight.device))
-    _lib.check(st, "ryolo_conv_pack_weights")
+    st = _lib.lib.ryolo_conv_pack_weights_ex(ctypes.byref(desc), _lib.ptr(w), _lib.ptr(s) if s is not None else None,
+                                             _lib.ptr(out), mode, _lib.stream_ptr(weight.device))
+    _lib.check(st, "ryolo_conv_pack_weights_ex")
     return out
 
 

@@ -158,6 +158,12 @@ class TrainPlan:
                         blk.ddesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cout, blk.cout_pad, blk.cin, blk.gsrc.cs,
                                                 blk.k, 1, False, 0.0, False, blk.gsrc.cs, False, False)
                 blk.dw = torch.zeros((blk.k_eff * blk.k_eff, blk.cout_pad, blk.cin_pad), dtype=torch.float32, device=device)
+                blk.pw = torch.empty(_lib.lib.ryolo_conv_packed_weight_bytes(ctypes.byref(blk.fdesc)), dtype=torch.uint8,
+                                     device=device)
+                if i > 0:
+                    blk.pwd = torch.empty(_lib.lib.ryolo_conv_packed_weight_bytes(ctypes.byref(blk.ddesc)), dtype=torch.uint8,
+                                          device=device)
+                blk.gw = torch.empty(tuple(seq.Conv2d.weight.shape), dtype=torch.float32, device=device)
                 blocks.append(blk)
                 i += 2 if (blk.fuse_res or blk.fuse_up) else 1
                 continue
@@ -207,9 +213,8 @@ class TrainPlan:
             if blk.s2d:
                 _lib.check(lib.ryolo_space_to_depth(ctypes.c_void_p(blk.src.ptr), blk.src.cs, self.batch, blk.src.h, blk.src.w,
                                                     blk.src.c, _lib.ptr(blk.xs), blk.xs_cs, st), "s2d")
-                w = L.s2d_weight(w)
                 x_ptr = blk.xs.data_ptr()
-            blk.pw = L.pack_weights(blk.fdesc, w)
+            L.pack_weights(blk.fdesc, w, None, 2 if blk.s2d else 0, out=blk.pw)
             if blk.is_head:
                 bias = L.padded_bias(blk.fdesc, seq.Conv2d.bias.detach())
                 _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.fdesc), ctypes.c_void_p(x_ptr), _lib.ptr(blk.pw),
@@ -279,17 +284,16 @@ class TrainPlan:
                     pgrads[(blk.i, "activation.weight")] = blk.bsums[2 * blk.cout:]
                 dz = blk.z
             blk.dw.zero_()
-            k = blk.k_eff
+            w = seq.Conv2d.weight.detach()
             if blk.s2d:
                 _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.cout_pad, blk.cout_pad, _lib.ptr(blk.xs), blk.xs_cs,
                                                 blk.cin_pad, self.batch, blk.src.h // 2, blk.src.w // 2, 2, _lib.ptr(blk.dw),
                                                 st), "wgrad s2d")
-                gw2 = blk.dw.view(2, 2, blk.cout_pad, blk.cin_pad)[:, :, :blk.cout, :blk.cin_eff].permute(2, 3, 0, 1)
-                pgrads[(blk.i, "Conv2d.weight")] = L.s2d_weight_grad(gw2, blk.src.c)
-                w2 = L.s2d_weight(seq.Conv2d.weight.detach())
-                wd = w2.flip(2, 3).permute(1, 0, 2, 3).contiguous()      # [4C, cout, 2, 2], taps mirrored (offsets 0..+1)
-                pwd = L.pack_weights(blk.ddesc, wd)
-                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(pwd),
+                _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 2, blk.cout, blk.src.c, 3,
+                                                       _lib.ptr(blk.gw), st), "unpack wgrad s2d")
+                pgrads[(blk.i, "Conv2d.weight")] = blk.gw
+                L.pack_weights(blk.ddesc, w, None, 3, out=blk.pwd)          # mirrored 2x2 taps, transposed, in the pack kernel
+                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(blk.pwd),
                                                      _lib.ptr(self.zero_bias), None, _lib.ptr(blk.dxs), None, 0, st), "dgrad s2d")
                 _lib.check(lib.ryolo_depth_to_space(_lib.ptr(blk.dxs), blk.xs_cs, self.batch, blk.src.h, blk.src.w, blk.src.c,
                                                     ctypes.c_void_p(blk.gsrc.ptr), blk.gsrc.cs, int(blk.gsrc_acc), st), "d2s")
@@ -301,15 +305,14 @@ class TrainPlan:
             _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.cout_pad, blk.cout_pad, ctypes.c_void_p(blk.src.ptr), blk.src.cs,
                                             blk.cin_pad, self.batch, blk.src.h, blk.src.w, blk.k_eff, _lib.ptr(blk.dw), st),
                        "wgrad")
-            gw = blk.dw.view(k, k, blk.cout_pad, blk.cin_pad)[:, :, :blk.cout, :blk.cin].permute(2, 3, 0, 1)
-            pgrads[(blk.i, "Conv2d.weight")] = gw.reshape(seq.Conv2d.weight.shape).clone()
+            _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 0, blk.cout, blk.cin, blk.k_eff,
+                                                   _lib.ptr(blk.gw), st), "unpack wgrad")
+            pgrads[(blk.i, "Conv2d.weight")] = blk.gw
             if blk.i > 0:
-                w = seq.Conv2d.weight.detach()
-                wd = w.flip(2, 3).permute(1, 0, 2, 3).contiguous()        # [cin, cout, k, k], taps mirrored
-                pwd = L.pack_weights(blk.ddesc, wd)
                 gp = blk.gsrc.ptr
                 blk.ddesc.has_residual = int(blk.gsrc_acc)
-                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(pwd),
+                L.pack_weights(blk.ddesc, w, None, 1, out=blk.pwd)          # taps mirrored + transposed in the pack kernel
+                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(blk.pwd),
                                                      _lib.ptr(self.zero_bias), ctypes.c_void_p(gp) if blk.gsrc_acc else None,
                                                      ctypes.c_void_p(gp), None, 0, st), "dgrad")
         out = []

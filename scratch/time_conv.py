@@ -4,6 +4,8 @@ import helpers, rotate_yolov3_b200 as pkg
 from rotate_yolov3_b200 import cfgs
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 m = pkg.Darknet(cfgs.yolov3_cfg(), {'context_factor': 1.0}); helpers.init_darknet_weights(m, 1); m = m.cuda().eval()
+import os
+m.use_cuda_graph = os.environ.get('GRAPH','0') == '1'
 x = torch.rand(B, 3, 608, 608, device='cuda')
 with torch.no_grad():
     io, ps = m(x); torch.cuda.synchronize()
