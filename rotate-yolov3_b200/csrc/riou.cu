@@ -68,12 +68,15 @@ __device__ __forceinline__ float clamp_integral_area(const RBox& a, const RBox& 
     cyp[i] = fminf(fmaxf(py[i], -hh), hh);
   }
   float acc = 0.f;
+  // edge vectors are +2u, +2v, -2u, -2v: four reciprocals serve the eight x/y breakpoint slopes
+  const float ru_x = __fdividef(0.5f, ux), ru_y = __fdividef(0.5f, uy), rv_x = __fdividef(0.5f, vx), rv_y = __fdividef(0.5f, vy);
 #pragma unroll
   for (int e = 0; e < 4; e++) {
     const int f = (e + 1) & 3;
     const float ax = px[e], ay = py[e];
     const float ex = px[f] - ax, ey = py[f] - ay;
-    const float rex = __fdividef(1.f, ex), rey = __fdividef(1.f, ey);
+    const float rex = e == 0 ? ru_x : (e == 1 ? rv_x : (e == 2 ? -ru_x : -rv_x));
+    const float rey = e == 0 ? ru_y : (e == 1 ? rv_y : (e == 2 ? -ru_y : -rv_y));
     // breakpoints (clamped to [0,1]; NaN from 0*inf is dropped by fmaxf/fminf)
     float t0 = fminf(fmaxf((-hw - ax) * rex, 0.f), 1.f);
     float t1 = fminf(fmaxf((hw - ax) * rex, 0.f), 1.f);
@@ -159,7 +162,7 @@ __device__ __forceinline__ RBox load_rbox(const float4* p0, const float4* p1, in
   return b;
 }
 
-__global__ void __launch_bounds__(RIOU_THREADS, 3) riou_pairwise_kernel(const float* __restrict__ a, int n, int sa,
+__global__ void __launch_bounds__(RIOU_THREADS, 4) riou_pairwise_kernel(const float* __restrict__ a, int n, int sa,
                                                                         const float* __restrict__ b, int m, int sb,
                                                                         int mode, float* __restrict__ out) {
   __shared__ RiouSmem sm;
