@@ -152,16 +152,21 @@ def torch_port_forward(model, x, train):
             if hasattr(mod, "activation"):
                 y = F.prelu(y, mod.activation.weight)
             x = y
-            if model.module_defs[i + 1]["type"] == "yolo":
+            nxt = model.module_defs[i + 1]["type"] if i + 1 < len(model.module_defs) else None
+            if nxt == "yolo" or (not model.yolo_layers and not hasattr(mod, "BatchNorm2d") and not hasattr(mod, "activation")):
                 heads.append(y)
         elif t == "shortcut":
             x = x + outs[i + int(d["from"])]
         elif t == "upsample":
             x = F.interpolate(x, scale_factor=2, mode="nearest")
+        elif t == "maxpool":
+            x = mod(x)          # nn.MaxPool2d / Sequential(ZeroPad2d, MaxPool2d) exactly as create_modules builds them
         elif t == "route":
             ls = [l if l > 0 else i + l for l in (int(v) for v in d["layers"].split(","))]
             x = torch.cat([outs[l] for l in ls], 1) if len(ls) > 1 else outs[ls[0]]
         outs.append(x)
+    if not model.yolo_layers:
+        return heads
     res = []
     for hd, yi in zip(heads, model.yolo_layers):
         layer = model.module_list[yi]

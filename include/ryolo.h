@@ -248,6 +248,12 @@ int ryolo_space_to_depth(const void* x, int x_cstride, int batch, int h, int w, 
                          int xs_cstride, void* stream);
 int ryolo_depth_to_space(const void* dxs, int dxs_cstride, int batch, int h, int w, int c, void* gx,
                          int gx_cstride, int accumulate, void* stream);
+/* 2x2 max pooling of a padded-NHWC bf16 tensor (reference: the maxpool blocks of
+ * cfg/yolov3-tiny.cfg, model/models.py:79-87).  stride 2: [in_h/2, in_w/2] output; stride 1: same
+ * size, the window past the right/bottom edge reads the zero halo exactly like the reference's
+ * nn.ZeroPad2d((0,1,0,1)) + MaxPool2d(2, 1). */
+int ryolo_maxpool2x2(const void* x, int x_cstride, int batch, int in_h, int in_w, int c, int stride,
+                     void* y, int y_cstride, void* stream);
 /* fp32 NCHW [B,C,H,W] -> bf16 padded NHWC interior, channels [0,C) (head gradients). */
 int ryolo_nchw_to_padded(const float* src, int batch, int c, int h, int w, void* dst,
                          int dst_cstride, void* stream);

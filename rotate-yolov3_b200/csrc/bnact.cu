@@ -349,6 +349,31 @@ __global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16
   *reinterpret_cast<uint4*>(gp) = pack8(d);
 }
 
+// 2x2 max pooling on padded NHWC (reference: nn.MaxPool2d(2, stride) blocks of cfg/yolov3-tiny.cfg, model/models.py:79-87).
+// stride 2: out[y, x] = max over in[2y..2y+1, 2x..2x+1].  stride 1: the reference zero-pads right/bottom
+// (nn.ZeroPad2d((0,1,0,1))) and pools with stride 1 -> out[y, x] = max over in[y..y+1, x..x+1] where the row/column past
+// the edge reads ZERO -- which is exactly the zero halo of the padded layout.
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const __nv_bfloat16* __restrict__ x, int xcs, int ih, int iw,
+                                                         Geo g /*output*/, int stride, __nv_bfloat16* __restrict__ y, int ycs) {
+  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int b, oy, ox, cg;
+  if (!decode_item(g, item, b, oy, ox, cg)) return;
+  const int y0 = oy * stride, x0 = ox * stride;
+  __nv_bfloat162 m[4];
+  bool first = true;
+#pragma unroll
+  for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+    for (int dx = 0; dx < 2; dx++) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + pad_off(b, y0 + dy, x0 + dx, ih, iw, xcs) + cg * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; e++) m[e] = first ? h[e] : __hmax2(m[e], h[e]);
+      first = false;
+    }
+  *reinterpret_cast<uint4*>(y + pad_off(b, oy, ox, g.h, g.w, ycs) + cg * 8) = *reinterpret_cast<uint4*>(m);
+}
+
 // fp32 NCHW [B, C, H, W] -> bf16 padded NHWC (interior, channels [0, C)).  Thread = (pixel x, 8-channel group):
 // consecutive threads read consecutive x of the same channel plane (coalesced) and write 16 bytes each.
 __global__ void __launch_bounds__(256) nchw_to_padded_kernel(const float* __restrict__ src, int batch, int c, int h, int w,
@@ -537,6 +562,20 @@ extern "C" int ryolo_depth_to_space(const void* dxs, int dxs_cstride, int batch,
   depth_to_space_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dxs),
                                                                             dxs_cstride, g, static_cast<__nv_bfloat16*>(gx),
                                                                             gx_cstride, accumulate);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_maxpool2x2(const void* x, int x_cstride, int batch, int in_h, int in_w, int c, int stride, void* y,
+                                int y_cstride, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(x && y && batch > 0 && in_h > 0 && in_w > 0 && c > 0 && c % 8 == 0);
+  RYOLO_ARG_CHECK(stride == 1 || (stride == 2 && in_h % 2 == 0 && in_w % 2 == 0));
+  const Geo g = mk_geo(batch, stride == 2 ? in_h / 2 : in_h, stride == 2 ? in_w / 2 : in_w, c);
+  const size_t items = n_items(g);
+  maxpool2x2_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_cstride, in_h,
+                                                                        in_w, g, stride, static_cast<__nv_bfloat16*>(y),
+                                                                        y_cstride);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }

@@ -221,6 +221,11 @@ class Darknet(nn.Module):
                 c, h, w = int(d["filters"]), (h + s - 1) // s, (w + s - 1) // s
             elif t == "upsample":
                 h, w = h * int(d["stride"]), w * int(d["stride"])
+            elif t == "maxpool":
+                if int(d["size"]) != 2 or int(d["stride"]) not in (1, 2):
+                    raise NotImplementedError("only the 2x2 max pools of yolov3-tiny have a kernel")
+                if int(d["stride"]) == 2:
+                    h, w = h // 2, w // 2
             elif t == "route":
                 ls = [int(x) for x in d["layers"].split(",")]
                 ls = [l if l > 0 else i + l for l in ls]
@@ -284,7 +289,8 @@ class Darknet(nn.Module):
                     continue
                 fuse_res = nxt == "shortcut" and i not in self.routes
                 fuse_up = nxt == "upsample" and i not in self.routes and int(defs[i + 1]["stride"]) == 2
-                is_head = nxt == "yolo"
+                # head = the linear, BN-less conv feeding a YOLO layer (or, in YOLO-less trunk graphs, any such conv)
+                is_head = nxt == "yolo" or (not self.yolo_layers and slope is None and not hasattr(self.module_list[i], "BatchNorm2d"))
                 mat = i + 1 if (fuse_res or fuse_up) else i       # the layer index whose output is materialised
                 if src.c != wt.shape[1]:
                     raise RuntimeError("channel mismatch at block %d" % i)
@@ -326,7 +332,13 @@ class Darknet(nn.Module):
                                            keep=(src, res, views[mat] if not is_head else out))))
                 i += 2 if (fuse_res or fuse_up) else 1
                 continue
-            if t == "route":
+            if t == "maxpool":
+                src = views[i - 1]
+                v = out_view(i)
+                steps.append(("maxpool", dict(x=src.ptr, xcs=src.cs, h=src.h, w=src.w, c=src.c, stride=int(d["stride"]),
+                                              y=v.ptr, ycs=v.cs, keep=(src, v))))
+                views[i] = v
+            elif t == "route":
                 ls = [int(x) for x in d["layers"].split(",")]
                 ls = [l if l > 0 else i + l for l in ls]
                 if len(ls) == 1:
@@ -380,7 +392,11 @@ class Darknet(nn.Module):
             lib = _lib.lib
             stream = _lib.stream_ptr(x.device)
             for kind, a in plan["steps"]:
-                if kind == "s2d":
+                if kind == "maxpool":
+                    st = lib.ryolo_maxpool2x2(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"], a["stride"],
+                                              ctypes.c_void_p(a["y"]), a["ycs"], stream)
+                    _lib.check(st, "ryolo_maxpool2x2")
+                elif kind == "s2d":
                     st = lib.ryolo_space_to_depth(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"],
                                                   _lib.ptr(a["xs"]), a["xs"].shape[-1], stream)
                     _lib.check(st, "ryolo_space_to_depth")
@@ -394,6 +410,8 @@ class Darknet(nn.Module):
                                                    _lib.ptr(a["b"]), ctypes.c_void_p(a["r"]) if a["r"] else None,
                                                    ctypes.c_void_p(a["y"]), None, 0, stream)
                     _lib.check(st, "ryolo_conv_bn_act_fwd")
+            if not self.yolo_layers:      # trunk graph without YOLO layers: the raw head maps [B, filters, ny, nx]
+                return [head for _, head in plan["heads"]]
             nc = self.module_list[self.yolo_layers[0]].nc
             total = sum(plan["rows"])
             io = torch.empty((b, total, nc + 6), dtype=torch.float32, device=x.device)
