@@ -397,6 +397,24 @@ def main():
         savl["dp%d" % k_] = p.grad.numpy()
     np.savez_compressed(os.path.join(HERE, "loss_golden.npz"), **savl)
     print("loss golden:", items.numpy())
+
+    # ---- 10. Darknet .weights written by the reference's save_weights (model/model_utils.py:96-118) ----
+    import model.model_utils as rmu
+    micro = ("[net]\nwidth=32\nheight=32\nchannels=3\n\n[convolutional]\nbatch_normalize=1\nfilters=8\nsize=3\nstride=1\npad=1\n"
+             "activation=leaky\n\n[convolutional]\nbatch_normalize=1\nfilters=16\nsize=3\nstride=2\npad=1\nactivation=leaky\n\n"
+             "[convolutional]\nfilters=14\nsize=1\nstride=1\npad=1\nactivation=linear\n\n[yolo]\nmask = 0-1\nanchors = ara 900 / 5.0 / -45, 45\n"
+             "classes=1\nnum=2\n\n")
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(micro)
+        cfg_path = f.name
+    mw = rmodels.Darknet(cfg_path, {"context_factor": 1.0}, arc="default")
+    helpers.init_darknet_weights(mw, seed=9)
+    mw.seen = np.array([1234], dtype=np.int64)
+    wpath = os.path.join(HERE, "micro_reference.weights")
+    rmu.save_weights(mw, wpath)
+    with open(os.path.join(HERE, "micro.cfg"), "w") as f:
+        f.write(micro)
+    print("weights golden:", os.path.getsize(wpath), "bytes")
     print("mini golden: loss %.4f, %d grads" % (float(lm), len([k for k in savm if k.startswith("grad:")])))
     print("train golden: loss %.4f, %d params, grad norm range %.3e .. %.3e" % (float(loss), len(names), min(norms), max(norms)))
 

@@ -102,3 +102,32 @@ def test_full_size_config2_properties():
     # paired kernel agrees with the matrix kernel
     p = pkg.skew_bbox_iou(a, b)
     assert float((p - m.diagonal()).abs().max()) < 1e-6
+
+
+def test_match_detections_vs_reference_loop():
+    """device-batched mAP matching (metrics.match_detections) vs a direct restatement of test.py:134-151 driven by the
+    float64 oracle IoU"""
+    from rotate_yolov3_b200.metrics import match_detections
+    g = torch.Generator().manual_seed(4)
+    tb = gen_boxes(12, 50, 200.0)
+    tcls = torch.randint(0, 3, (12,), generator=g).float()
+    pb = torch.cat([tb[torch.randint(0, 12, (40,), generator=g)] + 3.0 * torch.randn(40, 5, generator=g) * torch.tensor([1, 1, 1, 1, 0.01]),
+                    gen_boxes(20, 51, 200.0)], 0)
+    conf = torch.rand(60, generator=g).sort(descending=True).values
+    pcls = torch.randint(0, 4, (60,), generator=g).float()
+    pred = torch.cat([pb, conf[:, None], torch.ones(60, 1), pcls[:, None]], 1)
+    got = match_detections(pred.cuda(), tb.cuda(), tcls.cuda(), iou_thres=0.3)
+    iou = orc_skew_pairwise(pb.numpy(), tb.numpy())
+    want, detected = [0] * 60, []
+    for i in range(60):
+        if len(detected) == 12:
+            break
+        if float(pcls[i]) not in set(tcls.tolist()):
+            continue
+        m = (tcls == pcls[i]).nonzero().view(-1)
+        row = torch.from_numpy(iou[i])[m]
+        best, bi = row.max(0)
+        if float(best) > 0.3 and int(m[bi]) not in detected:
+            want[i] = 1
+            detected.append(int(m[bi]))
+    assert got == want and sum(got) > 3
