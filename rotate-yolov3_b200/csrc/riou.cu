@@ -20,6 +20,8 @@
 // Stage A2: separating-axis test on queue 1 with converged warps -> queue 2 (~12 % of all pairs).  Stage B: clamp
 // integral on queue 2.  The output tile lives in shared memory (pre-zeroed) and is written back with 128-bit
 // streaming stores, so HBM sees exactly one coalesced write of the matrix.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ryolo {
@@ -162,6 +164,7 @@ __device__ __forceinline__ RBox load_rbox(const float4* p0, const float4* p1, in
   return b;
 }
 
+template <int STORE>   // 0: streaming (st.global.cs), 1: plain, 2: write-through (st.global.wt)
 __global__ void __launch_bounds__(RIOU_THREADS, 4) riou_pairwise_kernel(const float* __restrict__ a, int n, int sa,
                                                                         const float* __restrict__ b, int m, int sb,
                                                                         int mode, float* __restrict__ out) {
@@ -264,7 +267,10 @@ __global__ void __launch_bounds__(RIOU_THREADS, 4) riou_pairwise_kernel(const fl
     for (int e = tid; e < rows * (CT / 4); e += RIOU_THREADS) {
       const int r = e / (CT / 4), c4 = e % (CT / 4);
       const float4 v = *reinterpret_cast<const float4*>(&sm.out[r * CT + c4 * 4]);
-      __stcs(reinterpret_cast<float4*>(out + (size_t)(r0 + r) * m + c0 + c4 * 4), v);  // streaming store
+      float4* dst = reinterpret_cast<float4*>(out + (size_t)(r0 + r) * m + c0 + c4 * 4);
+      if (STORE == 0) __stcs(dst, v);        // streaming: the matrix is written once and not re-read by this kernel
+      else if (STORE == 1) *dst = v;
+      else __stwt(dst, v);
     }
   } else {
     for (int e = tid; e < rows * CT; e += RIOU_THREADS) {
@@ -299,7 +305,15 @@ extern "C" int ryolo_riou_pairwise(const float* a, int n, int stride_a, const fl
   RYOLO_ARG_CHECK(a && b && out);
   dim3 grid((m + CT - 1) / CT, (n + RT - 1) / RT);
   RYOLO_ARG_CHECK(grid.y <= 65535);
-  riou_pairwise_kernel<<<grid, RIOU_THREADS, 0, stream>>>(a, n, stride_a, b, m, stride_b, mode, out);
+  static int store_mode = -1;
+  if (store_mode < 0) {   // measurement knob (profiles/): RYOLO_RIOU_STORE=0|1|2, default streaming stores
+    const char* e = getenv("RYOLO_RIOU_STORE");
+    store_mode = e ? atoi(e) : 0;
+    if (store_mode < 0 || store_mode > 2) store_mode = 0;
+  }
+  if (store_mode == 1) riou_pairwise_kernel<1><<<grid, RIOU_THREADS, 0, stream>>>(a, n, stride_a, b, m, stride_b, mode, out);
+  else if (store_mode == 2) riou_pairwise_kernel<2><<<grid, RIOU_THREADS, 0, stream>>>(a, n, stride_a, b, m, stride_b, mode, out);
+  else riou_pairwise_kernel<0><<<grid, RIOU_THREADS, 0, stream>>>(a, n, stride_a, b, m, stride_b, mode, out);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }
