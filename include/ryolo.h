@@ -151,7 +151,7 @@ typedef struct ryolo_conv_desc {
   int32_t batch;       /* B                                                                   */
   int32_t in_h, in_w;  /* input spatial size (unpadded)                                       */
   int32_t cin;         /* channels read by this conv                                          */
-  int32_t cin_stride;  /* channel stride of the input buffer (>= round_up(cin, 64))           */
+  int32_t cin_stride;  /* channel stride of the input buffer (>= cin, multiple of 8)           */
   int32_t cout;        /* filters                                                             */
   int32_t cout_stride; /* channel stride of the bf16 output buffer (>= round_up(cout, 32); channels
                           [cout, round_up(cout,32)) are written as zeros, nothing beyond)     */

@@ -524,7 +524,8 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   RYOLO_ARG_CHECK(!d->has_residual || (residual != nullptr && d->stride == 1 && !d->upsample2x &&
                                         d->res_stride % 8 == 0 && d->out_dtype == RYOLO_DT_BF16));
   const ConvGeom g = conv_geom(d);
-  RYOLO_ARG_CHECK(d->cin_stride >= g.cin_pad && d->cin_stride % 8 == 0);  // 64-wide K chunks read the channel padding
+  // a buffer narrower than the 64-wide K chunk is fine: TMA zero-fills the part of the box beyond the inner extent
+  RYOLO_ARG_CHECK(d->cin_stride >= d->cin && d->cin_stride % 8 == 0);
   RYOLO_ARG_CHECK(d->out_dtype == RYOLO_DT_BF16 || d->out_dtype == RYOLO_DT_F32);
   if (d->out_dtype == RYOLO_DT_BF16) RYOLO_ARG_CHECK(d->cout_stride % 8 == 0 && d->cout_stride >= round_up(d->cout, 32));
   RYOLO_ARG_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
@@ -558,7 +559,8 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   p.out = y;
 
   CUtensorMap ma, mb;
-  int st = encode_map_2d(&ma, x, (uint64_t)g.cin_pad, (uint64_t)p.np, (uint64_t)d->cin_stride * 2, BK, BM);
+  const int a_inner = d->cin_stride < g.cin_pad ? d->cin_stride : g.cin_pad;
+  int st = encode_map_2d(&ma, x, (uint64_t)a_inner, (uint64_t)p.np, (uint64_t)d->cin_stride * 2, BK, BM);
   if (st != RYOLO_OK) return st;
   st = encode_map_2d(&mb, packed_w, (uint64_t)g.cin_pad, (uint64_t)g.taps * g.cout_pad, (uint64_t)g.cin_pad * 2, BK,
                      (uint32_t)g.bn);

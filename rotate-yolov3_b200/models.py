@@ -262,8 +262,7 @@ class Darknet(nn.Module):
             if layer in target:
                 buf, off = target[layer]
                 return _View(buf, off, cc, hh, ww)
-            bn_ = 256 if cc > 128 else (128 if cc > 64 else 64)
-            return _View(L.alloc_padded(batch, hh, ww, L.round_up(cc, bn_), device), 0, cc, hh, ww)
+            return _View(L.alloc_padded(batch, hh, ww, L.round_up(cc, 32), device), 0, cc, hh, ww)
 
         steps = []
         heads = []

@@ -75,8 +75,7 @@ class TrainPlan:
             if layer in target:
                 buf, gbuf, off = target[layer]
             else:
-                bn_ = 256 if cc > 128 else (128 if cc > 64 else 64)
-                buf, gbuf = alloc_pair(hh, ww, L.round_up(cc, bn_))
+                buf, gbuf = alloc_pair(hh, ww, L.round_up(cc, 32))
                 off = 0
             return _mk_view(buf, off, cc, hh, ww), _mk_view(gbuf, off, cc, hh, ww)
 
@@ -111,15 +110,16 @@ class TrainPlan:
                 blk.is_head = nxt == "yolo"
                 blk.mat = i + 1 if (blk.fuse_res or blk.fuse_up) else i
                 bn_ = 256 if blk.cout > 128 else (128 if blk.cout > 64 else 64)
-                blk.cout_pad = L.round_up(blk.cout, bn_)
+                blk.cout_pad = L.round_up(blk.cout, bn_)     # GEMM tile extent (weights / dW)
+                blk.zcs = L.round_up(blk.cout, 32)           # channel stride of z / dz (TMA zero-fills up to the tile)
                 blk.cin = blk.src.c
                 blk.cin_pad = L.round_up(blk.cin, 64)
                 if blk.is_head:
                     blk.out = torch.empty((batch, blk.cout, blk.oh, blk.ow), dtype=torch.float32, device=device)
-                    blk.dz = L.alloc_padded(batch, blk.oh, blk.ow, blk.cout_pad, device)   # gradient of the head output
+                    blk.dz = L.alloc_padded(batch, blk.oh, blk.ow, blk.zcs, device)   # gradient of the head output
                     blk.res = blk.gres = None
                 else:
-                    blk.z = L.alloc_padded(batch, blk.oh, blk.ow, blk.cout_pad, device)     # raw conv output / dz
+                    blk.z = L.alloc_padded(batch, blk.oh, blk.ow, blk.zcs, device)     # raw conv output / dz
                     blk.y, blk.gy = out_views(blk.mat)
                     views[blk.mat], gviews[blk.mat] = blk.y, blk.gy
                     if blk.fuse_res:
@@ -142,20 +142,20 @@ class TrainPlan:
                     blk.k_eff = 2
                     blk.cin_eff, blk.cin_pad = 4 * blk.src.c, blk.xs_cs
                     blk.fdesc = L.make_desc(batch, blk.src.h // 2, blk.src.w // 2, blk.cin_eff, blk.xs_cs, blk.cout,
-                                            0 if blk.is_head else blk.cout_pad, 2, 1, False, 0.0, False, 0, False, blk.is_head)
-                    blk.ddesc = L.make_desc(batch, blk.src.h // 2, blk.src.w // 2, blk.cout, blk.cout_pad, blk.cin_eff,
+                                            0 if blk.is_head else blk.zcs, 2, 1, False, 0.0, False, 0, False, blk.is_head)
+                    blk.ddesc = L.make_desc(batch, blk.src.h // 2, blk.src.w // 2, blk.cout, blk.zcs, blk.cin_eff,
                                             blk.xs_cs, -2, 1, False, 0.0, False, 0, False, False)
                 else:
                     blk.cin_eff = blk.cin
                     if blk.stride == 2:
-                        blk.dz_up = L.alloc_padded(batch, blk.src.h, blk.src.w, blk.cout_pad, device)  # zero-inserted dz
+                        blk.dz_up = L.alloc_padded(batch, blk.src.h, blk.src.w, blk.zcs, device)  # zero-inserted dz
                     # forward descriptor: raw conv (no bias / activation); heads keep their bias and write fp32 NCHW
                     blk.fdesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cin, blk.src.cs, blk.cout,
-                                            0 if blk.is_head else blk.cout_pad, blk.k_eff, blk.stride, False, 0.0, False, 0,
+                                            0 if blk.is_head else blk.zcs, blk.k_eff, blk.stride, False, 0.0, False, 0,
                                             False, blk.is_head)
                     if i > 0:
                         # dgrad: stride-1 conv of dz (at the INPUT resolution) with mirrored taps / transposed weights
-                        blk.ddesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cout, blk.cout_pad, blk.cin, blk.gsrc.cs,
+                        blk.ddesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cout, blk.zcs, blk.cin, blk.gsrc.cs,
                                                 blk.k, 1, False, 0.0, False, blk.gsrc.cs, False, False)
                 blk.dw = torch.zeros((blk.k_eff * blk.k_eff, blk.cout_pad, blk.cin_pad), dtype=torch.float32, device=device)
                 blk.pw = torch.empty(_lib.lib.ryolo_conv_packed_weight_bytes(ctypes.byref(blk.fdesc)), dtype=torch.uint8,
@@ -226,7 +226,7 @@ class TrainPlan:
             cnt = n_per_pixel * blk.oh * blk.ow
             if blk.has_bn:
                 bn = seq.BatchNorm2d
-                _lib.check(lib.ryolo_bn_stats(_lib.ptr(blk.z), blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout,
+                _lib.check(lib.ryolo_bn_stats(_lib.ptr(blk.z), blk.zcs, self.batch, blk.oh, blk.ow, blk.cout,
                                               _lib.ptr(blk.sums), st), "bn_stats")
                 _lib.check(lib.ryolo_bn_finalize(_lib.ptr(blk.sums), blk.cout, cnt, bn.eps, bn.momentum, _lib.ptr(bn.weight),
                                                  _lib.ptr(bn.bias), _lib.ptr(blk.mean), _lib.ptr(blk.invstd),
@@ -237,7 +237,7 @@ class TrainPlan:
                 raise NotImplementedError("conv block without BatchNorm that is not a YOLO head")
             if not blk.has_act:
                 blk.slope = 1.0
-            _lib.check(lib.ryolo_bn_act_fwd(_lib.ptr(blk.z), blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout,
+            _lib.check(lib.ryolo_bn_act_fwd(_lib.ptr(blk.z), blk.zcs, self.batch, blk.oh, blk.ow, blk.cout,
                                             _lib.ptr(blk.scale), _lib.ptr(blk.shift), blk.slope, int(blk.has_act),
                                             ctypes.c_void_p(blk.res.ptr) if blk.res is not None else None,
                                             blk.res.cs if blk.res is not None else 0, ctypes.c_void_p(blk.y.ptr), blk.y.cs,
@@ -265,14 +265,14 @@ class TrainPlan:
             g_nchw = g.permute(0, 1, 4, 2, 3).reshape(self.batch, blk.cout, blk.oh, blk.ow).contiguous().float()
             pgrads[(blk.i, "Conv2d.bias")] = g_nchw.sum((0, 2, 3))
             _lib.check(lib.ryolo_nchw_to_padded(_lib.ptr(g_nchw), self.batch, blk.cout, blk.oh, blk.ow, _lib.ptr(blk.dz),
-                                                blk.cout_pad, st), "nchw_to_padded")
+                                                blk.zcs, st), "nchw_to_padded")
         for blk in reversed(self.blocks):
             seq = m.module_list[blk.i]
             if blk.is_head:
                 dz = blk.dz
             else:
                 _lib.check(lib.ryolo_bn_act_bwd(ctypes.c_void_p(blk.gy.ptr), blk.gy.cs, int(blk.fuse_up), _lib.ptr(blk.z),
-                                                blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout, _lib.ptr(blk.scale),
+                                                blk.zcs, self.batch, blk.oh, blk.ow, blk.cout, _lib.ptr(blk.scale),
                                                 _lib.ptr(blk.shift), _lib.ptr(blk.mean), _lib.ptr(blk.invstd), blk.slope,
                                                 int(blk.has_act), 1, _lib.ptr(blk.bsums),
                                                 ctypes.c_void_p(blk.gres.ptr) if blk.gres is not None else None,
@@ -286,7 +286,7 @@ class TrainPlan:
             blk.dw.zero_()
             w = seq.Conv2d.weight.detach()
             if blk.s2d:
-                _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.cout_pad, blk.cout_pad, _lib.ptr(blk.xs), blk.xs_cs,
+                _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.zcs, blk.cout_pad, _lib.ptr(blk.xs), blk.xs_cs,
                                                 blk.cin_pad, self.batch, blk.src.h // 2, blk.src.w // 2, 2, _lib.ptr(blk.dw),
                                                 st), "wgrad s2d")
                 _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 2, blk.cout, blk.src.c, 3,
@@ -299,10 +299,10 @@ class TrainPlan:
                                                     ctypes.c_void_p(blk.gsrc.ptr), blk.gsrc.cs, int(blk.gsrc_acc), st), "d2s")
                 continue
             if blk.stride == 2:
-                _lib.check(lib.ryolo_zero_insert2x(_lib.ptr(dz), blk.cout_pad, self.batch, blk.oh, blk.ow, blk.cout_pad,
-                                                   _lib.ptr(blk.dz_up), blk.cout_pad, blk.src.h, blk.src.w, st), "zero_insert")
+                _lib.check(lib.ryolo_zero_insert2x(_lib.ptr(dz), blk.zcs, self.batch, blk.oh, blk.ow, blk.zcs,
+                                                   _lib.ptr(blk.dz_up), blk.zcs, blk.src.h, blk.src.w, st), "zero_insert")
                 dz = blk.dz_up
-            _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.cout_pad, blk.cout_pad, ctypes.c_void_p(blk.src.ptr), blk.src.cs,
+            _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.zcs, blk.cout_pad, ctypes.c_void_p(blk.src.ptr), blk.src.cs,
                                             blk.cin_pad, self.batch, blk.src.h, blk.src.w, blk.k_eff, _lib.ptr(blk.dw), st),
                        "wgrad")
             _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 0, blk.cout, blk.cin, blk.k_eff,

@@ -22,7 +22,7 @@ def _ref(x, w, b, stride, slope, act, res=None, up=False):
 
 
 def _run(batch, h, w, cin, cout, k, stride=1, act=True, residual=False, up=False, f32=False, seed=0, cin_extra=0,
-         cout_extra=0):
+         cout_extra=0, narrow=False):
     from rotate_yolov3_b200 import layout as L
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -32,13 +32,15 @@ def _run(batch, h, w, cin, cout, k, stride=1, act=True, residual=False, up=False
     slope = 0.1
     oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
     cin_cs = L.round_up(cin, 64) + cin_extra
+    if narrow:                                   # 32-channel-granular buffers: TMA zero-fills the rest of the K chunk
+        cin_cs = L.round_up(cin, 32)
     xb = L.to_padded_nhwc(x, cin_cs)
     if cin_extra:
         xb[..., L.round_up(cin, 64):] = 7.0      # neighbouring channels of a concat buffer must not leak in
     desc = L.make_desc(batch, h, w, cin, cin_cs, cout, 0, k, stride, act, slope, residual, 0, up, f32)
     bn = 256 if cout > 128 else (128 if cout > 64 else 64)
     cout_pad = L.round_up(cout, bn)
-    cout_cs = cout_pad + cout_extra
+    cout_cs = L.round_up(cout, 32) if narrow else cout_pad + cout_extra
     desc.cout_stride = cout_cs
     res_t, res_buf = None, None
     if residual:
@@ -70,8 +72,8 @@ def _run(batch, h, w, cin, cout, k, stride=1, act=True, residual=False, up=False
         # halo untouched (zero), channel padding zero, neighbours of a wider buffer untouched
         assert float(y[:, 0].abs().max()) == 0 and float(y[:, -1].abs().max()) == 0
         assert float(y[:, :, 0].abs().max()) == 0 and float(y[:, :, -1].abs().max()) == 0
-        if cout_pad > cout and not cout_extra:
-            assert float(y[:, 1:-1, 1:-1, cout:cout_pad].abs().max()) == 0     # zero-initialised, chunk-padded or untouched
+        if cout_cs > cout and not cout_extra:
+            assert float(y[:, 1:-1, 1:-1, cout:cout_cs].abs().max()) == 0     # zero-initialised, chunk-padded or untouched
         if cout_extra:
             assert float((y[:, 1:-1, 1:-1, (cout + 31) // 32 * 32:] - 3.0).abs().max()) == 0
     return err
@@ -89,6 +91,9 @@ def _run(batch, h, w, cin, cout, k, stride=1, act=True, residual=False, up=False
     dict(batch=2, h=19, w=19, cin=64, cout=32, k=1, cin_extra=128),                 # cout padded 32->64, wide input buffer
     dict(batch=1, h=19, w=19, cin=512, cout=1024, k=3),                             # 4 n-tiles x 72 k-steps
     dict(batch=2, h=12, w=16, cin=64, cout=32, k=1, up=True, cout_extra=64),        # 32 filters at offset 0 of a wider (concat) buffer: neighbours intact
+    dict(batch=2, h=20, w=16, cin=32, cout=64, k=3, narrow=True),                   # 32-channel input buffer (stride 32 < K chunk)
+    dict(batch=2, h=20, w=16, cin=64, cout=32, k=1, narrow=True),                   # 32-channel output buffer
+    dict(batch=1, h=10, w=12, cin=160, cout=96, k=3, narrow=True),                  # strides 160 / 96: partial last K chunk
 ])
 def test_conv_block_vs_torch(cfg):
     _run(**cfg)
@@ -122,6 +127,8 @@ def test_first_layer_direct_conv():
     dict(batch=1, h=20, w=16, cin=32, cout=64, k=3),        # channel padding on the K... N side (cin 32 -> 64)
     dict(batch=2, h=19, w=19, cin=768, cout=256, k=1),      # cin_pad 768 = 3 n-tiles of 256
     dict(batch=4, h=38, w=38, cin=128, cout=504, k=1),      # cout_pad 512
+    dict(batch=2, h=20, w=16, cin=32, cout=32, k=3, narrow=True),    # both operands in 32-channel buffers
+    dict(batch=2, h=10, w=12, cin=160, cout=96, k=1, narrow=True),   # strides 160 / 96 (not tile multiples)
 ])
 def test_conv_wgrad_vs_torch(cfg):
     """tcgen05 wgrad (K = pixels, MN-major operands, split-K atomics) vs torch.nn.grad.conv2d_weight in fp32 on the
@@ -137,10 +144,12 @@ def test_conv_wgrad_vs_torch(cfg):
     cin_pad = L.round_up(cin, 64)
     bn = 256 if cout > 128 else (128 if cout > 64 else 64)
     cout_pad = L.round_up(cout, bn)
-    xb = L.to_padded_nhwc(x, cin_pad)
-    dzb = L.to_padded_nhwc(dz, cout_pad)
+    xcs = L.round_up(cin, 32) if cfg.get("narrow") else cin_pad
+    zcs = L.round_up(cout, 32) if cfg.get("narrow") else cout_pad
+    xb = L.to_padded_nhwc(x, xcs)
+    dzb = L.to_padded_nhwc(dz, zcs)
     dw = torch.zeros((k * k, cout_pad, cin_pad), dtype=torch.float32, device=dev)
-    st = pkg._lib.lib.ryolo_conv_wgrad(pkg._lib.ptr(dzb), cout_pad, cout_pad, pkg._lib.ptr(xb), cin_pad, cin_pad, b, h, w, k,
+    st = pkg._lib.lib.ryolo_conv_wgrad(pkg._lib.ptr(dzb), zcs, cout_pad, pkg._lib.ptr(xb), xcs, cin_pad, b, h, w, k,
                                        pkg._lib.ptr(dw), pkg._lib.stream_ptr(dev))
     assert st == 0, pkg._lib.last_error()
     torch.cuda.synchronize()
