@@ -191,12 +191,19 @@ size_t ryolo_conv_workspace_bytes(const ryolo_conv_desc* d);
 int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, const void* packed_w,
                           const float* bias, const void* residual, void* y, void* workspace,
                           size_t workspace_bytes, void* stream);
-/* First layer (cin = 3, 3x3, stride 1): fp32 NCHW image [B,3,H,W] -> bf16 padded NHWC with
- * channel stride cout_stride (channels >= cout zero-filled).  weight [cout,3,3,3] fp32 with BN
- * folded, bias [cout].  Direct CUDA-core kernel: K = 27 is too thin for the tensor pipe. */
+/* First layer (cin = 3, 3x3, stride 1; reference model/models.py:45-74 block 0): fp32 NCHW image
+ * [B,3,H,W] -> bf16 padded NHWC with channel stride cout_stride (channels >= cout zero-filled).
+ * weight [cout,3,3,3] fp32 with BN folded (rounded to bf16 in the kernel like every other layer's
+ * weights), bias [cout], cout = 16 | 32.  The im2col row of each pixel is built in registers
+ * (image split into bf16 hi + lo halves: 16 mantissa bits) and contracted with tcgen05.mma.
+ * ryolo_conv_first_s2d_fwd writes the same values straight into the space-to-depth buffer of a
+ * following 3x3/stride-2 layer (layout of ryolo_space_to_depth; H, W even; xs_cstride >= 4*cout). */
 int ryolo_conv_first_fwd(const float* img, int batch, int h, int w, const float* weight,
                          const float* bias, int cout, float slope, void* y, int cout_stride,
                          void* stream);
+int ryolo_conv_first_s2d_fwd(const float* img, int batch, int h, int w, const float* weight,
+                             const float* bias, int cout, float slope, void* xs, int xs_cstride,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * Training path of the conv blocks (reference: autograd through nn.Conv2d / BatchNorm2d / PReLU,

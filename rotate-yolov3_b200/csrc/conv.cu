@@ -330,57 +330,6 @@ __global__ void conv_unpack_wgrad_kernel(const float* __restrict__ dw, int cout_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// first layer: fp32 NCHW image, cin = 3, 3x3 / stride 1 / pad 1 -> bf16 padded NHWC (cout real + zero pad channels)
-// ---------------------------------------------------------------------------------------------------------------
-template <int COUT>
-__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ img, int batch, int h, int w,
-                                                         const float* __restrict__ weight, const float* __restrict__ bias,
-                                                         float slope, __nv_bfloat16* __restrict__ out, int out_cs) {
-  __shared__ float s_w[COUT * 27];
-  __shared__ float s_b[COUT];
-  for (int i = threadIdx.x; i < COUT * 27; i += blockDim.x) s_w[i] = weight[i];
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_b[i] = bias[i];
-  __syncthreads();
-  const size_t npix = (size_t)batch * h * w;
-  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= npix) return;
-  const int x = (int)(pix % w);
-  const int y = (int)((pix / w) % h);
-  const int b = (int)(pix / ((size_t)w * h));
-  float in[27];
-#pragma unroll
-  for (int c = 0; c < 3; c++)
-#pragma unroll
-    for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-      for (int dx = 0; dx < 3; dx++) {
-        const int yy = y + dy - 1, xx = x + dx - 1;
-        in[c * 9 + dy * 3 + dx] =
-            (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(img + (((size_t)b * 3 + c) * h + yy) * w + xx) : 0.f;
-      }
-  __nv_bfloat16* o = out + (((size_t)b * (h + 2) + y + 1) * (w + 2) + x + 1) * out_cs;
-#pragma unroll 1
-  for (int co = 0; co < COUT; co += 8) {
-    __nv_bfloat162 hv[4];
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-      float a0 = s_b[co + 2 * e], a1 = s_b[co + 2 * e + 1];
-#pragma unroll
-      for (int k = 0; k < 27; k++) {
-        a0 = fmaf(in[k], s_w[(co + 2 * e) * 27 + k], a0);
-        a1 = fmaf(in[k], s_w[(co + 2 * e + 1) * 27 + k], a1);
-      }
-      a0 = a0 > 0.f ? a0 : slope * a0;
-      a1 = a1 > 0.f ? a1 : slope * a1;
-      hv[e] = __floats2bfloat162_rn(a0, a1);
-    }
-    *reinterpret_cast<uint4*>(o + co) = *reinterpret_cast<uint4*>(hv);
-  }
-  // zero the padding channels [COUT, out_cs) so that the next layer's 64-wide K chunk reads zeros
-  for (int co = COUT; co < out_cs; co += 8) *reinterpret_cast<uint4*>(o + co) = make_uint4(0, 0, 0, 0);
-}
-
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct ConvGeom {
@@ -570,20 +519,3 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   return launch_conv<64>(ma, mb, p, stream);
 }
 
-extern "C" int ryolo_conv_first_fwd(const float* img, int batch, int h, int w, const float* weight, const float* bias,
-                                    int cout, float slope, void* y, int cout_stride, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  RYOLO_ARG_CHECK(img && weight && bias && y && batch > 0 && h > 0 && w > 0);
-  RYOLO_ARG_CHECK(cout == 32 || cout == 16);
-  RYOLO_ARG_CHECK(cout_stride >= cout && cout_stride % 8 == 0);
-  const size_t npix = (size_t)batch * h * w;
-  const unsigned blocks = (unsigned)((npix + 255) / 256);
-  if (cout == 32)
-    conv_first_kernel<32><<<blocks, 256, 0, stream>>>(img, batch, h, w, weight, bias, slope,
-                                                      static_cast<__nv_bfloat16*>(y), cout_stride);
-  else
-    conv_first_kernel<16><<<blocks, 256, 0, stream>>>(img, batch, h, w, weight, bias, slope,
-                                                      static_cast<__nv_bfloat16*>(y), cout_stride);
-  RYOLO_LAUNCH_CHECK();
-  return RYOLO_OK;
-}

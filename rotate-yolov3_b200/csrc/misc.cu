@@ -137,40 +137,61 @@ __global__ void __launch_bounds__(FT) nms_filter_write_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------
 // YOLO head decode (reference model/models.py:198-227)
 // ------------------------------------------------------------------------------------------------
+// One thread decodes one (b, anchor, y, x) cell.  The head tensor is NCHW (plane-strided, coalesced reads across x);
+// the two outputs are row-major [.., no] -- a CTA's 256 cells form ONE contiguous range of 256*no floats in each, so
+// the rows are staged in shared memory and written back with fully coalesced stores (the direct per-thread row store
+// touches every 32-B sector of the range `no` times with 4 useful bytes each).
+template <bool STAGED>
 __global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ p, int bs, int na, int nc, int ny,
                                                           int nx, const float* __restrict__ anchors, float stride,
                                                           float ctx, int arc_default, float* __restrict__ io,
                                                           int rows_total, int row_offset, float* __restrict__ p_out) {
+  constexpr int NO_MAX = 8;
+  __shared__ float s_io[STAGED ? 256 * NO_MAX : 1];
+  __shared__ float s_p[STAGED ? 256 * NO_MAX : 1];
   const int no = nc + 6;
-  const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over bs*na*ny*nx
-  const size_t total = (size_t)bs * na * ny * nx;
-  if (cell >= total) return;
-  const int x = (int)(cell % nx);
-  const int y = (int)((cell / nx) % ny);
-  const int a = (int)((cell / ((size_t)nx * ny)) % na);
-  const int b = (int)(cell / ((size_t)nx * ny * na));
+  const int per_img = na * ny * nx;
+  const int b = blockIdx.y;
+  const int cell0 = blockIdx.x * 256;
+  const int cell = cell0 + threadIdx.x;              // within the image: (a, y, x)
+  const bool live = cell < per_img;
   const size_t plane = (size_t)ny * nx;
-  const float* src = p + ((size_t)b * na * no + (size_t)a * no) * plane + (size_t)y * nx + x;
-  float* dst = io + ((size_t)b * rows_total + row_offset + ((size_t)a * ny + y) * nx + x) * no;
-  float* pd = p_out ? p_out + cell * no : nullptr;
-  // anchor_vec = anchors / stride (model_utils.py:30-31), theta untouched
-  const float aw = anchors[a * 3 + 0] / stride, ah = anchors[a * 3 + 1] / stride, at = anchors[a * 3 + 2];
-  const float t0 = src[0], t1 = src[plane], t2 = src[2 * plane], t3 = src[3 * plane], t4 = src[4 * plane];
-  if (pd) { pd[0] = t0; pd[1] = t1; pd[2] = t2; pd[3] = t3; pd[4] = t4; }
-  float bx = (1.f / (1.f + expf(-t0)) + (float)x) * stride;   // (sigmoid + grid) * stride
-  float by = (1.f / (1.f + expf(-t1)) + (float)y) * stride;
-  float bw = (expf(t2) * aw) * stride;
-  float bh = (expf(t3) * ah) * stride;
-  const float th = atanf(t4) + at;
-  bh = bh / ctx;                    // io[..., 3] /= context_factor
-  bw = bw - bh * (ctx - 1.f);       // io[..., 2] -= io[..., 3] * (context_factor - 1)
-  dst[0] = bx; dst[1] = by; dst[2] = bw; dst[3] = bh; dst[4] = th;
-  for (int k = 5; k < no; k++) {
-    const float v = src[(size_t)k * plane];
-    if (pd) pd[k] = v;
-    float o = arc_default ? 1.f / (1.f + expf(-v)) : v;
-    if (nc == 1 && k == 6) o = 1.f;  // models.py:220-221
-    dst[k] = o;
+  float* io_base = io + ((size_t)b * rows_total + row_offset + cell0) * no;
+  float* p_base = p_out ? p_out + ((size_t)b * per_img + cell0) * no : nullptr;
+  if (live) {
+    const int x = cell % nx;
+    const int y = (cell / nx) % ny;
+    const int a = cell / (nx * ny);
+    const float* src = p + ((size_t)b * na * no + (size_t)a * no) * plane + (size_t)y * nx + x;
+    float* dst = STAGED ? s_io + threadIdx.x * no : io_base + (size_t)threadIdx.x * no;
+    float* pd = STAGED ? s_p + threadIdx.x * no : (p_base ? p_base + (size_t)threadIdx.x * no : nullptr);
+    // anchor_vec = anchors / stride (model_utils.py:30-31), theta untouched
+    const float aw = anchors[a * 3 + 0] / stride, ah = anchors[a * 3 + 1] / stride, at = anchors[a * 3 + 2];
+    const float t0 = src[0], t1 = src[plane], t2 = src[2 * plane], t3 = src[3 * plane], t4 = src[4 * plane];
+    if (pd) { pd[0] = t0; pd[1] = t1; pd[2] = t2; pd[3] = t3; pd[4] = t4; }
+    float bx = (1.f / (1.f + expf(-t0)) + (float)x) * stride;   // (sigmoid + grid) * stride
+    float by = (1.f / (1.f + expf(-t1)) + (float)y) * stride;
+    float bw = (expf(t2) * aw) * stride;
+    float bh = (expf(t3) * ah) * stride;
+    const float th = atanf(t4) + at;
+    bh = bh / ctx;                    // io[..., 3] /= context_factor
+    bw = bw - bh * (ctx - 1.f);       // io[..., 2] -= io[..., 3] * (context_factor - 1)
+    dst[0] = bx; dst[1] = by; dst[2] = bw; dst[3] = bh; dst[4] = th;
+    for (int k = 5; k < no; k++) {
+      const float v = src[(size_t)k * plane];
+      if (pd) pd[k] = v;
+      float o = arc_default ? 1.f / (1.f + expf(-v)) : v;
+      if (nc == 1 && k == 6) o = 1.f;  // models.py:220-221
+      dst[k] = o;
+    }
+  }
+  if (STAGED) {
+    __syncthreads();
+    const int nval = min(256, per_img - cell0) * no;
+    for (int e = threadIdx.x; e < nval; e += 256) {
+      io_base[e] = s_io[e];
+      if (p_base) p_base[e] = s_p[e];
+    }
   }
 }
 
@@ -220,9 +241,14 @@ extern "C" int ryolo_yolo_decode(const float* p, int bs, int na, int nc, int ny,
   RYOLO_ARG_CHECK(row_offset >= 0 && row_offset + na * ny * nx <= io_rows_total);
   const size_t total = (size_t)bs * na * ny * nx;
   if (total == 0) return RYOLO_OK;
-  const unsigned blocks = (unsigned)((total + 255) / 256);
-  yolo_decode_kernel<<<blocks, 256, 0, stream>>>(p, bs, na, nc, ny, nx, anchors, stride, context_factor, arc_default,
-                                                 io_out, io_rows_total, row_offset, p_out);
+  RYOLO_ARG_CHECK(bs <= 65535 && (size_t)na * ny * nx < (1u << 30));
+  dim3 grid((unsigned)((na * ny * nx + 255) / 256), (unsigned)bs);
+  if (nc + 6 <= 8)
+    yolo_decode_kernel<true><<<grid, 256, 0, stream>>>(p, bs, na, nc, ny, nx, anchors, stride, context_factor, arc_default,
+                                                       io_out, io_rows_total, row_offset, p_out);
+  else
+    yolo_decode_kernel<false><<<grid, 256, 0, stream>>>(p, bs, na, nc, ny, nx, anchors, stride, context_factor, arc_default,
+                                                        io_out, io_rows_total, row_offset, p_out);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }

@@ -145,11 +145,11 @@ class _View:
 
     @property
     def cs(self):
-        return self.buf.shape[-1]
+        return self.buf.shape[-1] if self.buf is not None else 0
 
     @property
-    def ptr(self):
-        return self.buf.data_ptr() + 2 * self.ch_off
+    def ptr(self):          # buf None: the activation exists only in a consumer's space-to-depth buffer
+        return self.buf.data_ptr() + 2 * self.ch_off if self.buf is not None else None
 
 
 class Darknet(nn.Module):
@@ -266,6 +266,7 @@ class Darknet(nn.Module):
 
         steps = []
         heads = []
+        first_xs = None
         i = 0
         while i < n:
             d = defs[i]
@@ -280,9 +281,17 @@ class Darknet(nn.Module):
                 if i == 0:
                     if not (k == 3 and s == 1 and wt.shape[1] == 3 and cout in (16, 32) and slope is not None):
                         raise NotImplementedError("first layer must be 3x3/1 conv, 3 -> 16|32 channels, leaky")
-                    v = out_view(0)
                     wf = (wt * scale.view(-1, 1, 1, 1)).contiguous() if scale is not None else wt.contiguous()
-                    steps.append(("first", dict(w=wf, b=bias.contiguous(), cout=cout, slope=slope, out=v)))
+                    nd = defs[1] if n > 1 else {}
+                    first_s2d = (nd.get("type") == "convolutional" and int(nd["size"]) == 3 and int(nd["stride"]) == 2
+                                 and height % 2 == 0 and width % 2 == 0 and 0 not in self.routes)
+                    v = out_view(0) if not first_s2d else _View(None, 0, cout, height, width)
+                    if first_s2d:
+                        # layer 0 feeds only the stride-2 layer 1: write its output directly in that layer's
+                        # space-to-depth layout (no [B, H+2, W+2, 32] tensor, no s2d pass over it)
+                        first_xs = L.alloc_padded(batch, height // 2, width // 2, L.round_up(4 * cout, 64), device)
+                    steps.append(("first", dict(w=wf, b=bias.contiguous(), cout=cout, slope=slope, out=v,
+                                                xs=first_xs if first_s2d else None)))
                     views[0] = v
                     i += 1
                     continue
@@ -298,8 +307,11 @@ class Darknet(nn.Module):
                 if use_s2d:
                     # 3x3/stride-2 as a 2x2-tap stride-1 conv on the space-to-depth copy of the input (1.78x instead of
                     # 4x MMA work; also removes the 32->64 channel padding of the first down-sampling layer)
-                    xs = L.alloc_padded(batch, src.h // 2, src.w // 2, L.round_up(4 * src.c, 64), device)
-                    steps.append(("s2d", dict(x=src.ptr, xcs=src.cs, h=src.h, w=src.w, c=src.c, xs=xs, keep=src)))
+                    if i == 1 and first_xs is not None:
+                        xs = first_xs                      # already written by the first-layer kernel
+                    else:
+                        xs = L.alloc_padded(batch, src.h // 2, src.w // 2, L.round_up(4 * src.c, 64), device)
+                        steps.append(("s2d", dict(x=src.ptr, xcs=src.cs, h=src.h, w=src.w, c=src.c, xs=xs, keep=src)))
                     desc = L.make_desc(batch, src.h // 2, src.w // 2, 4 * src.c, xs.shape[-1], cout, 0, 2, 1,
                                        slope is not None, slope if slope is not None else 0.0, fuse_res, 0, fuse_up, is_head)
                     wt = L.s2d_weight(wt)
@@ -400,9 +412,13 @@ class Darknet(nn.Module):
                                                   _lib.ptr(a["xs"]), a["xs"].shape[-1], stream)
                     _lib.check(st, "ryolo_space_to_depth")
                 elif kind == "first":
-                    v = a["out"]
-                    st = lib.ryolo_conv_first_fwd(_lib.ptr(x), b, h, w, _lib.ptr(a["w"]), _lib.ptr(a["b"]), a["cout"],
-                                                  a["slope"], ctypes.c_void_p(v.ptr), v.cs, stream)
+                    if a["xs"] is not None:
+                        st = lib.ryolo_conv_first_s2d_fwd(_lib.ptr(x), b, h, w, _lib.ptr(a["w"]), _lib.ptr(a["b"]),
+                                                          a["cout"], a["slope"], _lib.ptr(a["xs"]), a["xs"].shape[-1], stream)
+                    else:
+                        v = a["out"]
+                        st = lib.ryolo_conv_first_fwd(_lib.ptr(x), b, h, w, _lib.ptr(a["w"]), _lib.ptr(a["b"]), a["cout"],
+                                                      a["slope"], ctypes.c_void_p(v.ptr), v.cs, stream)
                     _lib.check(st, "ryolo_conv_first_fwd")
                 else:
                     st = lib.ryolo_conv_bn_act_fwd(ctypes.byref(a["desc"]), ctypes.c_void_p(a["x"]), _lib.ptr(a["w"]),

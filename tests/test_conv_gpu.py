@@ -99,25 +99,40 @@ def test_conv_block_vs_torch(cfg):
     _run(**cfg)
 
 
-def test_first_layer_direct_conv():
-    import ctypes
+@pytest.mark.parametrize("cout,cs,shape", [(32, 64, (2, 40, 56)), (32, 32, (3, 38, 50)), (16, 32, (1, 26, 26))])
+def test_first_layer_tensor_core_conv(cout, cs, shape):
+    """3 -> cout first layer on the tensor pipe (register im2col, image as bf16 hi+lo) vs an fp32 conv with the same
+    bf16-rounded weights: within one bf16 ulp of the output; padding channels and halo zero."""
     import rotate_yolov3_b200 as pkg
     from rotate_yolov3_b200 import layout as L
     dev = torch.device("cuda")
+    b, h, wd = shape
     g = torch.Generator().manual_seed(1)
-    x = torch.rand(2, 3, 40, 56, generator=g).to(dev)
-    w = (torch.randn(32, 3, 3, 3, generator=g) / 5).to(dev)
-    b = torch.randn(32, generator=g).to(dev)
-    y = L.alloc_padded(2, 40, 56, 64, dev)
-    y[:, 1:-1, 1:-1, 32:] = 5.0
-    st = pkg._lib.lib.ryolo_conv_first_fwd(pkg._lib.ptr(x), 2, 40, 56, pkg._lib.ptr(w), pkg._lib.ptr(b), 32, 0.1,
-                                           pkg._lib.ptr(y), 64, pkg._lib.stream_ptr(dev))
-    assert st == 0
-    want = _ref(x, w, b, 1, 0.1, True)
-    got = L.from_padded_nhwc(y, 32)
-    assert bool(((got - want).abs() <= 2.0 ** -8 * want.abs() + 1e-5).all())
-    assert float(y[..., 32:].abs().max()) == 0      # channel padding zeroed for the next layer's 64-wide K chunk
+    x = torch.rand(b, 3, h, wd, generator=g).to(dev)
+    w = (torch.randn(cout, 3, 3, 3, generator=g) / 5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    y = L.alloc_padded(b, h, wd, cs, dev)
+    y[:, 1:-1, 1:-1, cout:] = 5.0
+    st = pkg._lib.lib.ryolo_conv_first_fwd(pkg._lib.ptr(x), b, h, wd, pkg._lib.ptr(w), pkg._lib.ptr(bias), cout, 0.1,
+                                           pkg._lib.ptr(y), cs, pkg._lib.stream_ptr(dev))
+    assert st == 0, pkg._lib.last_error()
+    want = _ref(x, w.to(torch.bfloat16).float(), bias, 1, 0.1, True)
+    got = L.from_padded_nhwc(y, cout)
+    assert bool(((got - want).abs() <= 2.0 ** -8 * want.abs() + 2e-5).all()), float((got - want).abs().max())
+    if cs > cout:
+        assert float(y[..., cout:].abs().max()) == 0      # channel padding zeroed for the next layer's 64-wide K chunk
     assert float(y[:, 0].abs().max()) == 0 and float(y[:, :, 0].abs().max()) == 0
+    # the same values written straight into the space-to-depth layout of a following stride-2 layer
+    xs = L.alloc_padded(b, h // 2, wd // 2, L.round_up(4 * cout, 64), dev)
+    st = pkg._lib.lib.ryolo_conv_first_s2d_fwd(pkg._lib.ptr(x), b, h, wd, pkg._lib.ptr(w), pkg._lib.ptr(bias), cout, 0.1,
+                                               pkg._lib.ptr(xs), xs.shape[-1], pkg._lib.stream_ptr(dev))
+    assert st == 0, pkg._lib.last_error()
+    xs_want = L.alloc_padded(b, h // 2, wd // 2, L.round_up(4 * cout, 64), dev)
+    st = pkg._lib.lib.ryolo_space_to_depth(pkg._lib.ptr(y), cs, b, h, wd, cout, pkg._lib.ptr(xs_want), xs_want.shape[-1],
+                                           pkg._lib.stream_ptr(dev))
+    assert st == 0, pkg._lib.last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(xs, xs_want)
 
 
 @pytest.mark.parametrize("cfg", [
