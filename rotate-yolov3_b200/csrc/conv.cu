@@ -13,8 +13,8 @@
 // the tap offset; rows that fall outside [0, NP) are zero-filled by TMA.  No im2col buffer, no gather.  The GEMM
 // also produces values at halo positions; the epilogue simply does not store them.  Cost of that: (H+2)(W+2)/HW
 // extra MMA rows (5 % at 76^2, 11 % at 38^2, 22 % at 19^2).
-// Stride-2 layers (5 of 75) run the same stride-1 GEMM on the input grid and store only the even pixels
-// (v1: 4x MMA waste on 12 % of the FLOPs; a strided 3-D TMA box is the planned replacement).
+// Stride-2 3x3 layers run on a space-to-depth copy of their input as 2x2-tap stride-1 convs (ksize = 2); odd sizes
+// fall back to the stride-1 GEMM on the input grid that stores only the even pixels.
 //
 // Kernel.  Persistent, warp-specialised, one CTA per SM, tile = 128 pixels x BN filters, BK = 64 channels:
 //   warp 0   TMA producer: per k-step one A box (shifted by the tap offset) + one B box into a 128B-swizzled
@@ -22,11 +22,18 @@
 //   warp 1   MMA issuer: one elected thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
 //            per stage, accumulating in TMEM; tcgen05.commit releases the stage / publishes the accumulator;
 //   warp 2   TMEM allocator (2 accumulator stages x BN fp32 columns);
-//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time -> +bias -> PReLU -> +residual -> bf16 -> 64-byte
-//            contiguous stores per pixel (or fp32 NCHW for the three linear heads), overlapped with the next
-//            tile's MMAs through the second accumulator stage.
+//   warps 4-11 epilogue, two teams of four warps that alternate over 64-filter groups of the accumulator:
+//            tcgen05.ld -> +bias -> PReLU -> +residual -> bf16.  For the common case (bf16 output on the same padded
+//            grid) the group is staged in a 128B-swizzled shared-memory buffer and leaves through a TMA bulk store
+//            (whole 128-byte lines; halo rows staged as zeros), and the residual group ARRIVES in that same buffer
+//            through a TMA load prefetched one group ahead, so the epilogue has no exposed global-memory latency
+//            (measured: per-thread residual loads + 16-byte stores made the epilogue, not the MMA, the bottleneck of
+//            every 3x3 body layer).  Up-sampling producers and the fp32 NCHW heads keep per-thread stores.
+//            The epilogue overlaps the next tile's MMAs through the second accumulator stage.
 #include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc05.cuh"
@@ -35,7 +42,75 @@ namespace ryolo {
 
 constexpr int BM = 128;  // pixels per tile (UMMA M, TMEM lanes)
 constexpr int BK = 64;   // channels per k-step = one 128-byte swizzle row of bf16
-constexpr int CONV_THREADS = 256;
+constexpr int CONV_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: two epilogue teams
+
+// packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2): halves the instruction count of the epilogue math
+__device__ __forceinline__ uint64_t f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// 32 accumulator columns of one row -> +bias -> PReLU -> +residual -> 32 bf16 (four 16-byte chunks).
+// sb: the 32 biases (shared memory, warp-uniform address); res: the row's 128-byte staging line holding the residual
+// group (chunk c at c ^ sw), hf selects its lower / upper 32 filters.  act: 0 none, 1 slope in [0, 1] (max(x, s*x),
+// bit-identical to the select), 2 general slope.
+template <bool RES>
+__device__ __forceinline__ void epilogue_math32(const uint32_t (&v)[32], const float* sb, int act, float slope,
+                                                const unsigned char* res, int hf, int sw, uint4 (&pk)[4]) {
+  const uint64_t s2 = f32x2(slope, slope);
+#pragma unroll
+  for (int gg = 0; gg < 4; gg++) {
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + gg * 8), b1 = *reinterpret_cast<const float4*>(sb + gg * 8 + 4);
+    const uint64_t bb[4] = {f32x2(b0.x, b0.y), f32x2(b0.z, b0.w), f32x2(b1.x, b1.y), f32x2(b1.z, b1.w)};
+    uint4 rv = make_uint4(0, 0, 0, 0);
+    if (RES) rv = *reinterpret_cast<const uint4*>(res + (((hf * 4 + gg) ^ sw) << 4));
+    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      uint64_t x2 = add2(f32x2(__uint_as_float(v[gg * 8 + 2 * e]), __uint_as_float(v[gg * 8 + 2 * e + 1])), bb[e]);
+      float lo, hi;
+      if (act == 1) {
+        const uint64_t y2 = mul2(x2, s2);
+        float ylo, yhi;
+        f32x2_unpack(x2, lo, hi);
+        f32x2_unpack(y2, ylo, yhi);
+        lo = fmaxf(lo, ylo);
+        hi = fmaxf(hi, yhi);
+        if (RES) x2 = f32x2(lo, hi);
+      } else if (act == 2) {
+        f32x2_unpack(x2, lo, hi);
+        lo = lo > 0.f ? lo : slope * lo;
+        hi = hi > 0.f ? hi : slope * hi;
+        if (RES) x2 = f32x2(lo, hi);
+      } else {
+        f32x2_unpack(x2, lo, hi);
+      }
+      if (RES) {
+        // bf16x2 word: low half = even filter.  bf16 -> fp32 is a 16-bit shift.
+        x2 = add2(x2, f32x2(__uint_as_float(rw[e] << 16), __uint_as_float(rw[e] & 0xffff0000u)));
+        f32x2_unpack(x2, lo, hi);
+      }
+      const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+      o[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    pk[gg] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
 
 struct ConvParams {
   int np;             // B * (H+2) * (W+2): GEMM M
@@ -53,28 +128,37 @@ struct ConvParams {
   int store_cols;     // bf16 output: columns [0, store_cols) of the padded filter range are stored
   int res_cs;         // channel stride of the residual buffer
   int has_act, has_res, upsample2x, out_f32_nchw;
+  int tma_store;      // bf16 stride-1 non-upsampled output: tiles leave (and residuals arrive) through TMA, 64-filter groups
+  int dbg;            // measurement knob RYOLO_CONV_DEBUG (scratch/conv_exp.py): timing experiments only, 0 in production
   float slope;
   const float* bias;               // [cout_pad]
   const __nv_bfloat16* residual;   // padded NHWC like the output, or null
   void* out;
 };
 
-template <int BN>
+// NBUF = group buffers per epilogue team.  2 lets a residual group prefetch while the other buffer is processed; the
+// BN = 256 tile only has room for 4 pipeline stages with NBUF = 1, which is what its residual-free launches use.
+template <int BN, int NBUF>
 struct ConvSmem {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? (NBUF == 1 ? 4 : 3) : (BN == 128 ? 5 : 6);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTileBytes = kStages * kStageBytes;
-  static constexpr int kBarOffset = kTileBytes;                       // full[kStages], empty[kStages], tfull[2], tempty[2]
-  static constexpr int kBiasOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;
-  static constexpr int kTotal = kBiasOffset + BN * 4 + 1024 /*alignment slack*/;
+  static constexpr int kGroupBytes = BM * 128;                        // one [128 pixels x 64 filters] bf16 group
+  static constexpr int kStagingOffset = kTileBytes;                   // [team][buffer] group buffers
+  static constexpr int kBarOffset = kStagingOffset + 2 * NBUF * kGroupBytes;
+  // full[kStages], empty[kStages], tfull[2], tempty[2], rfull[4]
+  static constexpr int kNumBars = 2 * kStages + 8;
+  static constexpr int kBiasOffset = kBarOffset + kNumBars * 8 + 16;  // [team][64] fp32: bias of the team's current group
+  static constexpr int kTotal = kBiasOffset + 2 * 64 * 4 + 1024 /*alignment slack*/;
 };
 
-template <int BN>
+template <int BN, int NBUF>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvParams p) {
-  using S = ConvSmem<BN>;
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_r, const ConvParams p) {
+  using S = ConvSmem<BN, NBUF>;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -84,8 +168,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   auto empty_bar = [&](int s) { return bar_base + 8u * (S::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S::kStages + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOffset + (2 * S::kStages + 4) * 8);
-  float* s_bias = reinterpret_cast<float*>(smem_gen + S::kBiasOffset);
+  auto rfull_bar = [&](int i) { return bar_base + 8u * (2 * S::kStages + 4 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOffset + S::kNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -98,8 +182,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 8);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < 4; i++) mbar_init(rfull_bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -128,9 +213,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           else if (p.taps == 4) off = (tap / 2 - 1 + p.tap_flip) * p.wp + (tap % 2 - 1 + p.tap_flip);
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * S::kStageBytes;
-          mbar_expect_tx(full_bar(stage), S::kStageBytes);
-          tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, p0 + off);
-          tma_load_2d(sa + S::kABytes, &map_b, full_bar(stage), kc * BK, tap * p.cout_pad + nt * BN);
+          const bool skip_b = (p.dbg & 4) && !(tile == (int)blockIdx.x && kk < S::kStages);
+          const bool skip_a = (p.dbg & 8) && !(tile == (int)blockIdx.x && kk < S::kStages);
+          mbar_expect_tx(full_bar(stage), (skip_a ? 0 : S::kABytes) + (skip_b ? 0 : S::kBBytes));
+          if (!skip_a) tma_load_2d(sa, &map_a, full_bar(stage), kc * BK, p0 + off);
+          if (!skip_b) tma_load_2d(sa + S::kABytes, &map_b, full_bar(stage), kc * BK, tap * p.cout_pad + nt * BN);
           if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -156,7 +243,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / 16; k++) {
             // +32 bytes (16 bf16) along K inside the swizzle atom: start-address field += 2
-            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kk | k) != 0);
+            if (!(p.dbg & 16)) tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kk | k) != 0);
           }
           tc_commit(empty_bar(stage));  // frees the stage when these MMAs have read it
           if (kk == k_iters - 1) tc_commit(tfull_bar(acc));
@@ -166,18 +253,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // ===================== epilogue: two teams of four warps =====================
+    // A tile's accumulator is drained in 64-filter GROUPS; group G = it * (BN/64) + g belongs to team G & 1, so the
+    // two teams (one warp of each per SM sub-partition) overlap each other's TMEM-load / math / store latencies.
+    constexpr int GPT = BN / 64;                  // groups per tile
+    const int team = (warp - 4) >> 2;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                // tile row = TMEM lane
+    const int tid_t = threadIdx.x & 127;          // thread index within the team
+    const bool issuer = tid_t == 0;               // first thread of the team issues its TMA traffic
+    float* s_bias = reinterpret_cast<float*>(smem_gen + S::kBiasOffset) + team * 64;
+    const int act = !p.has_act ? 0 : ((p.slope >= 0.f && p.slope <= 1.f) ? 1 : 2);
+    const uint32_t bar_id = 1 + team;
+    auto team_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
-      // bias for this n-tile -> smem (epilogue warps only: named barrier 1, 128 threads)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 128; i < BN; i += 128) s_bias[i] = p.bias[nt * BN + i];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+    // TMA-store mode state: two group buffers per team, used alternately.  A buffer first receives the residual
+    // group (TMA load, prefetched one group ahead), is transformed in place by the team, and leaves through a TMA store.
+    int buf = 0;                 // buffer of the next group to process
+    uint32_t rphase[2] = {0, 0}; // parity of rfull[team*2 + b]
+    int pit = GPT == 1 ? team : 0, pg = GPT == 1 ? 0 : team;   // prefetch cursor over this team's groups
+    int pbuf = 0;
+    auto group_buf = [&](int b) { return S::kStagingOffset + (team * NBUF + b) * S::kGroupBytes; };
+    // issue the residual load of the next live group of this team.  Called when the team STARTS a group, for the group
+    // after it (into the other buffer), so the load has a whole group's processing time to land.
+    auto prefetch_residual = [&]() {
+      for (;;) {
+        const int tile = blockIdx.x + pit * gridDim.x;
+        if (tile >= total_tiles) return;
+        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        const int colbase = nt * BN + pg * 64;
+        const bool live = colbase < p.store_cols;
+        if (live && issuer) {
+          // the buffer's previous TMA store (the team's latest one) must have finished READING it
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_expect_tx(rfull_bar(team * 2 + pbuf), S::kGroupBytes);
+          tma_load_2d(smem_base + group_buf(pbuf), &map_r, rfull_bar(team * 2 + pbuf), colbase, mt * BM);
+        }
+        if (GPT == 1) pit += 2;
+        else { pg += 2; if (pg >= GPT) { pg = team; pit += 1; } }
+        if (live) { pbuf ^= (NBUF - 1); return; }
+      }
+    };
+    const bool tma_res = NBUF == 2 && p.tma_store && p.has_res && !(p.dbg & 64);
+    if (tma_res) prefetch_residual();
 
-      const int pix = mt * BM + q * 32 + lane;  // flat padded input-grid pixel of this thread's row
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      const int pix = mt * BM + row;  // flat padded input-grid pixel of this thread's row
       bool valid = pix < p.np;
       int b = 0, yp = 0, xp = 0;
       if (valid) {
@@ -198,65 +322,123 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-
       const int n_valid = min(BN, p.cout - nt * BN);  // real filters in this n-tile (may be <= 0 for pure padding)
+
+      if (p.tma_store) {
+        // The tile's rows ARE rows of the output buffer (same padded geometry): groups are staged in shared memory
+        // (128B-swizzled rows, conflict-free 16-byte accesses) and TMA writes whole 128-byte lines.  Halo rows are
+        // staged as zeros, so the halo stays zero; rows beyond the tensor / filters beyond store_cols are clipped by
+        // the tensor map.
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tc_ld32(t_row + c0, v);
-        tc_wait_ld();
-        if (!valid) continue;
-        if (!p.out_f32_nchw && nt * BN + c0 >= p.store_cols) continue;   // narrower output buffer than the padded tile
-        float f[32];
+        for (int g = (GPT == 1 ? 0 : team); g < GPT; g += (GPT == 1 ? 1 : 2)) {
+          if (GPT == 1 && (it & 1) != team) break;
+          const int colbase = nt * BN + g * 64;
+          if (colbase >= p.store_cols || (p.dbg & 2)) break;
+          const int halves = (p.store_cols - colbase) >= 64 ? 2 : 1;
+          uint32_t v0[32], v1[32];
+          tc_ld32(t_row + g * 64, v0);
+          if (halves == 2) tc_ld32(t_row + g * 64 + 32, v1);
+          unsigned char* srow = smem_gen + group_buf(buf) + row * 128;
+          if (tid_t < 64) s_bias[tid_t] = __ldg(p.bias + colbase + tid_t);   // this group's biases
+          if (tma_res) {
+            prefetch_residual();                                 // next group -> other buffer
+          } else if (issuer) {
+            // the previous TMA store out of this buffer (NBUF groups ago) must have finished reading it
+            if (NBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          team_sync();
+          if (tma_res) {
+            mbar_wait(rfull_bar(team * 2 + buf), rphase[buf]);   // residual group landed in this buffer
+            rphase[buf] ^= 1;
+          }
+          tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          float x = __uint_as_float(v[j]) + s_bias[c0 + j];
-          if (p.has_act) x = x > 0.f ? x : p.slope * x;
-          f[j] = x;
+          for (int hf = 0; hf < 2; hf++) {
+            if (hf >= halves) break;
+            uint4 pk[4];
+            if (valid) {
+              if (tma_res) epilogue_math32<true>(hf == 0 ? v0 : v1, s_bias + hf * 32, act, p.slope, srow, hf, row & 7, pk);
+              else epilogue_math32<false>(hf == 0 ? v0 : v1, s_bias + hf * 32, act, p.slope, srow, hf, row & 7, pk);
+            } else {
+#pragma unroll
+              for (int gg = 0; gg < 4; gg++) pk[gg] = make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int gg = 0; gg < 4; gg++) *reinterpret_cast<uint4*>(srow + (((hf * 4 + gg) ^ (row & 7)) << 4)) = pk[gg];
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          team_sync();
+          if (issuer && !(p.dbg & 1)) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&map_o)),
+                         "r"(smem_base + group_buf(buf)), "r"(colbase), "r"(mt * BM)
+                         : "memory");
+          }
+          if (issuer) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          buf ^= (NBUF - 1);
         }
-        if (p.out_f32_nchw) {
-          // heads: fp32 [B, cout, oh, ow]
-          float* o = reinterpret_cast<float*>(p.out);
-          const size_t plane = (size_t)p.oh * p.ow;
-          const size_t base = ((size_t)b * p.cout) * plane + (size_t)oy * p.ow + ox;
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (p.dbg & 2) break;
+          if (((c0 >> 5) & 1) != team) continue;   // 32-column chunks alternate between the teams
+          if (!p.out_f32_nchw && nt * BN + c0 >= p.store_cols) continue;   // narrower output buffer than the padded tile
+          uint32_t v[32];
+          tc_ld32(t_row + c0, v);
+          tc_wait_ld();
+          if (!valid || (p.dbg & 1)) continue;
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (c0 + j < n_valid) o[base + (size_t)(nt * BN + c0 + j) * plane] = f[j];
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
-          const int ohp = (p.upsample2x ? 2 * p.oh : p.oh) + 2, owp = (p.upsample2x ? 2 * p.ow : p.ow) + 2;
-          if (p.has_res) {
-            const __nv_bfloat16* r =
-                p.residual + (((size_t)b * (p.oh + 2) + oy + 1) * (p.ow + 2) + ox + 1) * p.res_cs + nt * BN + c0;
-            const uint4* r4 = reinterpret_cast<const uint4*>(r);
+          for (int j = 0; j < 32; j++) {
+            float x = __uint_as_float(v[j]) + __ldg(p.bias + nt * BN + c0 + j);   // warp-uniform address
+            if (p.has_act) x = x > 0.f ? x : p.slope * x;
+            f[j] = x;
+          }
+          if (p.out_f32_nchw) {
+            // heads: fp32 [B, cout, oh, ow]
+            float* o = reinterpret_cast<float*>(p.out);
+            const size_t plane = (size_t)p.oh * p.ow;
+            const size_t base = ((size_t)b * p.cout) * plane + (size_t)oy * p.ow + ox;
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-              const uint4 rv = __ldg(r4 + g);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+            for (int j = 0; j < 32; j++)
+              if (c0 + j < n_valid) o[base + (size_t)(nt * BN + c0 + j) * plane] = f[j];
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+            const int ohp = (p.upsample2x ? 2 * p.oh : p.oh) + 2, owp = (p.upsample2x ? 2 * p.ow : p.ow) + 2;
+            if (p.has_res) {
+              const __nv_bfloat16* r =
+                  p.residual + (((size_t)b * (p.oh + 2) + oy + 1) * (p.ow + 2) + ox + 1) * p.res_cs + nt * BN + c0;
+              const uint4* r4 = reinterpret_cast<const uint4*>(r);
 #pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const float2 ff = __bfloat1622float2(h[e]);
-                f[g * 8 + e * 2] += ff.x;
-                f[g * 8 + e * 2 + 1] += ff.y;
+              for (int g = 0; g < 4; g++) {
+                const uint4 rv = __ldg(r4 + g);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                  const float2 ff = __bfloat1622float2(h[e]);
+                  f[g * 8 + e * 2] += ff.x;
+                  f[g * 8 + e * 2 + 1] += ff.y;
+                }
               }
             }
-          }
-          uint4 pk[4];
+            uint4 pk[4];
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
-            __nv_bfloat162 h[4];
+            for (int g = 0; g < 4; g++) {
+              __nv_bfloat162 h[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(f[g * 8 + e * 2], f[g * 8 + e * 2 + 1]);
-            pk[g] = *reinterpret_cast<uint4*>(h);
-          }
-          const int reps = p.upsample2x ? 2 : 1;
-          for (int ry = 0; ry < reps; ry++)
-            for (int rx = 0; rx < reps; rx++) {
-              const int yy = (p.upsample2x ? 2 * oy + ry : oy) + 1, xx = (p.upsample2x ? 2 * ox + rx : ox) + 1;
-              uint4* o4 = reinterpret_cast<uint4*>(o + (((size_t)b * ohp + yy) * owp + xx) * p.out_cs + nt * BN + c0);
-#pragma unroll
-              for (int g = 0; g < 4; g++) o4[g] = pk[g];
+              for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(f[g * 8 + e * 2], f[g * 8 + e * 2 + 1]);
+              pk[g] = *reinterpret_cast<uint4*>(h);
             }
+            const int reps = p.upsample2x ? 2 : 1;
+            for (int ry = 0; ry < reps; ry++)
+              for (int rx = 0; rx < reps; rx++) {
+                const int yy = (p.upsample2x ? 2 * oy + ry : oy) + 1, xx = (p.upsample2x ? 2 * ox + rx : ox) + 1;
+                uint4* o4 = reinterpret_cast<uint4*>(o + (((size_t)b * ohp + yy) * owp + xx) * p.out_cs + nt * BN + c0);
+#pragma unroll
+                for (int g = 0; g < 4; g++) o4[g] = pk[g];
+              }
+          }
         }
       }
       tc_fence_before();
@@ -264,6 +446,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores complete
   }
 
   tc_fence_before();
@@ -387,12 +570,13 @@ int encode_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t row
   return RYOLO_OK;
 }
 
-template <int BN>
-static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t stream) {
-  using S = ConvSmem<BN>;
+template <int BN, int NBUF>
+static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
+                       const ConvParams& p, cudaStream_t stream) {
+  using S = ConvSmem<BN, NBUF>;
   static bool attr_set = false;
   if (!attr_set) {
-    RYOLO_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    RYOLO_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -403,7 +587,7 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvP
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
-  conv_igemm_kernel<BN><<<grid, CONV_THREADS, S::kTotal, stream>>>(ma, mb, p);
+  conv_igemm_kernel<BN, NBUF><<<grid, CONV_THREADS, S::kTotal, stream>>>(ma, mb, mo, mr, p);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }
@@ -476,6 +660,7 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   // a buffer narrower than the 64-wide K chunk is fine: TMA zero-fills the part of the box beyond the inner extent
   RYOLO_ARG_CHECK(d->cin_stride >= d->cin && d->cin_stride % 8 == 0);
   RYOLO_ARG_CHECK(d->out_dtype == RYOLO_DT_BF16 || d->out_dtype == RYOLO_DT_F32);
+  RYOLO_ARG_CHECK(!d->has_residual || (reinterpret_cast<uintptr_t>(residual) & 15) == 0);
   if (d->out_dtype == RYOLO_DT_BF16) RYOLO_ARG_CHECK(d->cout_stride % 8 == 0 && d->cout_stride >= round_up(d->cout, 32));
   RYOLO_ARG_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
 
@@ -506,6 +691,12 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   p.bias = bias;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.out = y;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("RYOLO_CONV_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  p.dbg = dbg;
 
   CUtensorMap ma, mb;
   const int a_inner = d->cin_stride < g.cin_pad ? d->cin_stride : g.cin_pad;
@@ -514,8 +705,26 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   st = encode_map_2d(&mb, packed_w, (uint64_t)g.cin_pad, (uint64_t)g.taps * g.cout_pad, (uint64_t)g.cin_pad * 2, BK,
                      (uint32_t)g.bn);
   if (st != RYOLO_OK) return st;
-  if (g.bn == 256) return launch_conv<256>(ma, mb, p, stream);
-  if (g.bn == 128) return launch_conv<128>(ma, mb, p, stream);
-  return launch_conv<64>(ma, mb, p, stream);
+  // output map for the TMA-store epilogue: rows = flat padded pixels (same geometry as the input when stride is 1),
+  // inner extent = store_cols so that a wider (concat) buffer's neighbouring channels are never touched
+  CUtensorMap mo = ma;
+  p.tma_store = (d->out_dtype == RYOLO_DT_BF16 && d->stride == 1 && !d->upsample2x) ? 1 : 0;
+  if (dbg & 32) p.tma_store = 0;
+  if (p.tma_store) {
+    st = encode_map_2d(&mo, y, (uint64_t)p.store_cols, (uint64_t)p.np, (uint64_t)d->cout_stride * 2, 64, BM);
+    if (st != RYOLO_OK) return st;
+  }
+  CUtensorMap mr = ma;
+  if (p.tma_store && p.has_res) {
+    // residual groups arrive through TMA too (prefetched one group ahead); filters >= cout read as zero
+    st = encode_map_2d(&mr, residual, (uint64_t)d->cout, (uint64_t)p.np, (uint64_t)d->res_stride * 2, 64, BM);
+    if (st != RYOLO_OK) return st;
+  }
+  if (g.bn == 256) {
+    if (p.tma_store && p.has_res) return launch_conv<256, 2>(ma, mb, mo, mr, p, stream);
+    return launch_conv<256, 1>(ma, mb, mo, mr, p, stream);
+  }
+  if (g.bn == 128) return launch_conv<128, 2>(ma, mb, mo, mr, p, stream);
+  return launch_conv<64, 2>(ma, mb, mo, mr, p, stream);
 }
 
