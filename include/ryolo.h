@@ -233,15 +233,18 @@ int ryolo_bn_finalize(const float* sums, int c, float count, float eps, float mo
 int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, int w, int c,
                      const float* scale, const float* shift, float slope, int has_act,
                      const void* residual, int res_cstride, void* y, int y_cstride, int upsample2x,
-                     void* stream);
-/* Backward of the same block.  dy: gradient of y (at 2h x 2w when upsample2x).  z_dz: in = z, out =
+                     const float* slope_dev, void* stream);
+/* slope_dev (both directions, optional): device scalar holding the PReLU slope (nn.PReLU.weight);
+ * when non-null it replaces `slope`, so a training step never copies the parameter to the host.
+ * Backward of the same block.  dy: gradient of y (at 2h x 2w when upsample2x).  z_dz: in = z, out =
  * dz (gradient of the raw conv output, written in place).  sums (fp32 [2c+1], zeroed inside):
  * [0..c) = d(beta), [c..2c) = d(gamma), [2c] = d(slope).  gres (optional): gradient buffer of the
  * shortcut source, receives (+)= dy. */
 int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, void* z_dz, int z_cstride,
                      int batch, int h, int w, int c, const float* scale, const float* shift,
                      const float* mean, const float* invstd, float slope, int has_act, int has_bn,
-                     float* sums, void* gres, int gres_cstride, int gres_accumulate, void* stream);
+                     float* sums, void* gres, int gres_cstride, int gres_accumulate,
+                     const float* slope_dev, void* stream);
 /* Adjoint of a stride-2 conv's pixel selection: src (h x w) -> even interior pixels of the
  * pre-zeroed dst (dst_h x dst_w). */
 int ryolo_zero_insert2x(const void* src, int src_cstride, int batch, int h, int w, int c, void* dst,

@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(BNT) bn_act_fwd_kernel(const __nv_bfloat16* __
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          float slope, int has_act, const __nv_bfloat16* __restrict__ res,
                                                          int rcs, __nv_bfloat16* __restrict__ y, int ycs, int up,
-                                                         int rows_per_block) {
+                                                         int rows_per_block, const float* __restrict__ slope_dev) {
+  if (slope_dev) slope = __ldg(slope_dev);
   const RowSpan rs = row_span(g);
   float sc[8], sh[8];
   load8(scale, rs.cg, sc);
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(BNT) bn_act_bwd_reduce_kernel(const __nv_bfloa
                                                                 const float* __restrict__ mean,
                                                                 const float* __restrict__ invstd, float slope, int has_act,
                                                                 float* __restrict__ sums /*[2*c + 1]*/,
-                                                                int rows_per_block) {
+                                                                int rows_per_block, const float* __restrict__ slope_dev) {
+  if (slope_dev) slope = __ldg(slope_dev);
   extern __shared__ float s_acc[];  // [2 * c + 1]
   for (int i = threadIdx.x; i < 2 * g.c + 1; i += BNT) s_acc[i] = 0.f;
   __syncthreads();
@@ -232,7 +234,8 @@ __global__ void __launch_bounds__(BNT) bn_act_bwd_apply_kernel(const __nv_bfloat
                                                                const float* __restrict__ invstd, float slope, int has_act,
                                                                int has_bn, const float* __restrict__ sums, float inv_n,
                                                                __nv_bfloat16* __restrict__ gres, int gcs, int gres_acc,
-                                                               int rows_per_block) {
+                                                               int rows_per_block, const float* __restrict__ slope_dev) {
+  if (slope_dev) slope = __ldg(slope_dev);
   const RowSpan rs = row_span(g);
   float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
   load8(scale, rs.cg, sc);
@@ -469,7 +472,7 @@ extern "C" int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, in
 
 extern "C" int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, int w, int c, const float* scale,
                                 const float* shift, float slope, int has_act, const void* residual, int res_cstride,
-                                void* y, int y_cstride, int upsample2x, void* stream_) {
+                                void* y, int y_cstride, int upsample2x, const float* slope_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(z && scale && shift && y);
   GEO_CHECK();
@@ -479,7 +482,8 @@ extern "C" int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, 
   const int rpb = rows_per_block(g);
   bn_act_fwd_kernel<<<(unsigned)((batch * h + rpb - 1) / rpb), BNT, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(z), z_cstride, g, scale, shift, slope, has_act,
-      static_cast<const __nv_bfloat16*>(residual), res_cstride, static_cast<__nv_bfloat16*>(y), y_cstride, upsample2x, rpb);
+      static_cast<const __nv_bfloat16*>(residual), res_cstride, static_cast<__nv_bfloat16*>(y), y_cstride, upsample2x, rpb,
+      slope_dev);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }
@@ -487,7 +491,7 @@ extern "C" int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, 
 extern "C" int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, void* z_dz, int z_cstride, int batch, int h,
                                 int w, int c, const float* scale, const float* shift, const float* mean,
                                 const float* invstd, float slope, int has_act, int has_bn, float* sums, void* gres,
-                                int gres_cstride, int gres_accumulate, void* stream_) {
+                                int gres_cstride, int gres_accumulate, const float* slope_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(dy && z_dz && scale && shift && mean && invstd && sums);
   GEO_CHECK();
@@ -499,13 +503,13 @@ extern "C" int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, 
   const unsigned blocks = (unsigned)((batch * h + rpb - 1) / rpb);
   bn_act_bwd_reduce_kernel<<<blocks, BNT, (2 * c + 1) * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(dy), dy_cstride, upsample2x, static_cast<const __nv_bfloat16*>(z_dz), z_cstride, g,
-      scale, shift, mean, invstd, slope, has_act, sums, rpb);
+      scale, shift, mean, invstd, slope, has_act, sums, rpb, slope_dev);
   RYOLO_LAUNCH_CHECK();
   const float inv_n = 1.0f / ((float)batch * h * w);
   bn_act_bwd_apply_kernel<<<blocks, BNT, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(dy), dy_cstride, upsample2x, static_cast<__nv_bfloat16*>(z_dz), z_cstride, g, scale,
       shift, mean, invstd, slope, has_act, has_bn, sums, inv_n, static_cast<__nv_bfloat16*>(gres), gres_cstride,
-      gres_accumulate, rpb);
+      gres_accumulate, rpb, slope_dev);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }

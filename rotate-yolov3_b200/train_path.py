@@ -197,12 +197,16 @@ class TrainPlan:
         _lib.check(lib.ryolo_im2col_first(_lib.ptr(x), self.batch, self.h, self.w, _lib.ptr(self.col), st), "im2col")
         n_per_pixel = float(self.batch)
         heads = []
-        # all PReLU slopes in ONE device->host transfer (they are kernel scalars)
-        act_blocks = [b for b in self.blocks if b.has_act]
-        if act_blocks:
-            vals = torch.cat([m.module_list[b.i].activation.weight.detach().float().reshape(1) for b in act_blocks]).tolist()
-            for b, v in zip(act_blocks, vals):
-                b.slope = float(v)
+        # PReLU slopes stay on the device (kernels read nn.PReLU.weight through slope_dev): no host synchronisation
+        for b in self.blocks:
+            if b.has_act:
+                wgt = m.module_list[b.i].activation.weight
+                if wgt.numel() != 1 or wgt.dtype != torch.float32:
+                    raise NotImplementedError("PReLU with per-channel or non-fp32 slope")
+                b.slope_dev = wgt.data_ptr()
+            else:
+                b.slope_dev = None
+            b.slope = 1.0
         bn_counters = []
         for blk in self.blocks:
             seq = m.module_list[blk.i]
@@ -235,13 +239,11 @@ class TrainPlan:
                 bn_counters.append(bn.num_batches_tracked)
             else:
                 raise NotImplementedError("conv block without BatchNorm that is not a YOLO head")
-            if not blk.has_act:
-                blk.slope = 1.0
             _lib.check(lib.ryolo_bn_act_fwd(_lib.ptr(blk.z), blk.zcs, self.batch, blk.oh, blk.ow, blk.cout,
                                             _lib.ptr(blk.scale), _lib.ptr(blk.shift), blk.slope, int(blk.has_act),
                                             ctypes.c_void_p(blk.res.ptr) if blk.res is not None else None,
                                             blk.res.cs if blk.res is not None else 0, ctypes.c_void_p(blk.y.ptr), blk.y.cs,
-                                            int(blk.fuse_up), st), "bn_act_fwd")
+                                            int(blk.fuse_up), ctypes.c_void_p(blk.slope_dev), st), "bn_act_fwd")
         if bn_counters:
             with torch.no_grad():
                 torch._foreach_add_(bn_counters, 1)
@@ -276,7 +278,8 @@ class TrainPlan:
                                                 _lib.ptr(blk.shift), _lib.ptr(blk.mean), _lib.ptr(blk.invstd), blk.slope,
                                                 int(blk.has_act), 1, _lib.ptr(blk.bsums),
                                                 ctypes.c_void_p(blk.gres.ptr) if blk.gres is not None else None,
-                                                blk.gres.cs if blk.gres is not None else 0, int(blk.gres_acc), st),
+                                                blk.gres.cs if blk.gres is not None else 0, int(blk.gres_acc),
+                                                ctypes.c_void_p(blk.slope_dev), st),
                            "bn_act_bwd")
                 pgrads[(blk.i, "BatchNorm2d.bias")] = blk.bsums[:blk.cout]
                 pgrads[(blk.i, "BatchNorm2d.weight")] = blk.bsums[blk.cout:2 * blk.cout]

@@ -55,15 +55,17 @@ def test_bn_prelu_fwd_bwd_vs_autograd(c, h, w, b, res, up):
     shift = (beta - mean * scale).contiguous()
     yb = L.alloc_padded(b, oh, ow, cs, dev)
     rb = L.to_padded_nhwc(r, cs) if res else None
-    assert lib.ryolo_bn_act_fwd(pt(zb), cs, b, h, w, c, pt(scale), pt(shift), slope, 1, pt(rb) if res else None, cs, pt(yb),
-                                cs, int(up), stream) == 0
+    sd = torch.tensor([slope], device=dev)     # the slope as a device scalar (nn.PReLU.weight): overrides the host value
+    assert lib.ryolo_bn_act_fwd(pt(zb), cs, b, h, w, c, pt(scale), pt(shift), 123.0, 1, pt(rb) if res else None, cs, pt(yb),
+                                cs, int(up), pt(sd), stream) == 0
     got_y = L.from_padded_nhwc(yb, c)
     assert float((got_y - y.detach()).abs().max()) <= 2.0 ** -7 * float(y.abs().max())
     dyb = L.to_padded_nhwc(dy, cs)
     bs = torch.zeros(2 * c + 1, device=dev)
     grb = L.alloc_padded(b, h, w, cs, dev) if res else None
     assert lib.ryolo_bn_act_bwd(pt(dyb), cs, int(up), pt(zb), cs, b, h, w, c, pt(scale), pt(shift), pt(mean.contiguous()),
-                                pt(invstd.contiguous()), slope, 1, 1, pt(bs), pt(grb) if res else None, cs, 0, stream) == 0
+                                pt(invstd.contiguous()), slope if res else -7.0, 1, 1, pt(bs), pt(grb) if res else None, cs, 0,
+                                None if res else pt(sd), stream) == 0
     torch.cuda.synchronize()
     dz = L.from_padded_nhwc(zb, c)
     sc = float(zt.grad.abs().max())
