@@ -36,15 +36,43 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled from a thread
+    every 2 ms (an `nvidia-smi -lms` child needs ~0.3 s to produce its first line -- longer than most timed regions
+    here); nvidia-smi is the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.nvml, self.samples, self.reasons, self.stop_flag, self.mx = None, [], set(), False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = int(get_reasons(h))
+                        for bit, name in self.BITS.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.nvml = threading.Thread(target=poll, daemon=True)
+            self.nvml.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -59,6 +87,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.nvml.join(timeout=1)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml, 2 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -76,7 +110,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -337,7 +371,7 @@ def main():
         # BASELINE configs[3]: Darknet-53 training step, global batch 64 x 608 x 608 synthetic, compute_loss of the
         # reference (no rotated IoU in it), SGD nesterov; images shard across ranks, per-replica BN, ONE
         # NCCL all-reduce over the flattened gradients per step.
-        from rotate_yolov3_b200 import cfgs
+        from rotate_yolov3_b200 import cfgs, parallel
         from rotate_yolov3_b200.loss import compute_loss
         per_gpu = max(1, 64 // world)
         model = pkg.Darknet(cfgs.yolov3_cfg(), dict(TRAIN_HYP), arc="default")
@@ -369,12 +403,7 @@ def main():
             loss.backward()
             if timers:
                 timers[2].record()
-            if world > 1:
-                flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
-                dist.all_reduce(flat)
-                flat.div_(world)
-                for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
-                    p.grad.copy_(g)
+            parallel.allreduce_gradients(params)      # one flat NCCL all-reduce (no-op at world size 1)
             opt.step()
             if timers:
                 timers[3].record()
@@ -512,6 +541,13 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = units * world / (float(te.item()) * 1e-3) * scale
 
+    # one more step with stage timers.  EVERY rank runs it: the training step contains the gradient all-reduce, so a
+    # rank-0-only step would wait for peers that have already left.
+    if args.workload == "train":
+        tm = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        train_step(x, tg, tm)
+        torch.cuda.synchronize()
+        barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -519,9 +555,6 @@ def main():
 
     # ---------------- roofline of the dominant kernel ----------------
     if args.workload == "train":
-        tm = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        train_step(x, tg, tm)
-        torch.cuda.synchronize()
         stage_ms = {"forward": tm[0].elapsed_time(tm[1]), "loss_backward": tm[1].elapsed_time(tm[2]),
                     "allreduce_sgd": tm[2].elapsed_time(tm[3])}
         flops = 3 * 141.98e9 * per_gpu                 # fwd + dgrad + wgrad, convs only

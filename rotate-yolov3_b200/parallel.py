@@ -31,3 +31,19 @@ def max_over_ranks(value, device):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def allreduce_gradients(params):
+    """Data-parallel training (train.py:168-176 wraps the model in DistributedDataParallel): average the gradients of
+    `params` over the ranks with ONE all-reduce of the flattened buffer (NCCL on GPUs, gloo in the CPU tests).  Every rank
+    must call it the same number of times.  No-op without an initialised process group / with world size 1."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat)
+    flat.div_(dist.get_world_size())
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)

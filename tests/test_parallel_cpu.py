@@ -32,6 +32,15 @@ def _worker(rank, world, port, n_total):
     owner[lo:hi] += 1
     dist.all_reduce(owner)
     assert bool((owner == 1).all())
+    # data-parallel gradient averaging: one flat all-reduce, parameters without a gradient are skipped
+    params = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(1))]
+    params[0].grad = torch.full((3, 2), float(rank + 1))
+    params[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+    P.allreduce_gradients(params)
+    mean = sum(range(1, world + 1)) / world
+    assert torch.allclose(params[0].grad, torch.full((3, 2), mean))
+    assert torch.allclose(params[1].grad, torch.arange(5, dtype=torch.float32) * mean)
+    assert params[2].grad is None
     dist.destroy_process_group()
 
 
