@@ -267,6 +267,11 @@ int ryolo_maxpool2x2(const void* x, int x_cstride, int batch, int in_h, int in_w
 /* fp32 NCHW [B,C,H,W] -> bf16 padded NHWC interior, channels [0,C) (head gradients). */
 int ryolo_nchw_to_padded(const float* src, int batch, int c, int h, int w, void* dst,
                          int dst_cstride, void* stream);
+/* Gradient of a YOLO head in the layout autograd delivers it, fp32 [B, na, ny, nx, no] (training-mode
+ * head output, reference model/models.py:190-192), -> bf16 padded NHWC [B, ny+2, nx+2, dst_cstride]
+ * with channel = a*no + k (the head conv's filter index); channels >= na*no are left untouched. */
+int ryolo_head_grad_to_padded(const float* g, int batch, int na, int no, int ny, int nx, void* dst,
+                              int dst_cstride, void* stream);
 /* im2col of the 3-channel fp32 image for the first 3x3 conv: bf16 padded NHWC with 64 channels
  * (27 real, column = c*9 + kh*3 + kw), so that the first layer runs on the same GEMM kernels. */
 int ryolo_im2col_first(const float* img, int batch, int h, int w, void* dst, void* stream);

@@ -402,6 +402,38 @@ __global__ void __launch_bounds__(256) nchw_to_padded_kernel(const float* __rest
   }
 }
 
+// Gradient of a YOLO head as autograd delivers it, fp32 [B, na, ny, nx, no] (the layout of the training-mode output,
+// model/models.py:190-192), -> bf16 padded NHWC with channel = a * no + k (the head conv's filter index).  One block =
+// 32 consecutive x of one image row: coalesced reads of the 32*no contiguous floats of every anchor, transposed through
+// shared memory, 16-byte stores of each pixel's na*no contiguous channels.
+__global__ void __launch_bounds__(256) head_grad_to_padded_kernel(const float* __restrict__ g, int na, int no, int ny, int nx,
+                                                                  __nv_bfloat16* __restrict__ dst, int dcs) {
+  extern __shared__ __align__(16) unsigned char hg_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(hg_smem);   // [32][cpad]
+  const int c = na * no, cpad = (c + 7) & ~7;
+  const int x0 = blockIdx.x * 32, y = blockIdx.y, b = blockIdx.z;
+  const int npx = min(32, nx - x0);
+  const int run = npx * no;                                            // contiguous floats per anchor
+  for (int idx = threadIdx.x; idx < na * run; idx += 256) {
+    const int a = idx / run, r = idx - a * run;
+    const int px = r / no, k = r - px * no;
+    const float v = __ldg(g + (((size_t)b * na + a) * ny + y) * (size_t)nx * no + (size_t)x0 * no + r);
+    tile[px * cpad + a * no + k] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int chunks = c >> 3;                                           // whole 16-byte chunks per pixel
+  for (int idx = threadIdx.x; idx < npx * chunks; idx += 256) {
+    const int px = idx / chunks, ch = idx - px * chunks;
+    *reinterpret_cast<uint4*>(dst + pad_off(b, y, x0 + px, ny, nx, dcs) + ch * 8) =
+        *reinterpret_cast<const uint4*>(tile + px * cpad + ch * 8);
+  }
+  const int tail = c & 7;
+  for (int idx = threadIdx.x; idx < npx * tail; idx += 256) {
+    const int px = idx / tail, e = (c & ~7) + idx % tail;
+    dst[pad_off(b, y, x0 + px, ny, nx, dcs) + e] = tile[px * cpad + e];
+  }
+}
+
 // im2col of the 3-channel image for the first 3x3/stride-1/pad-1 conv: column index = c*9 + kh*3 + kw (the flattening
 // of nn.Conv2d.weight[co]), 27 real + zero padding to 64 channels, bf16 padded NHWC
 __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ img, int batch, int h, int w,
@@ -592,6 +624,25 @@ extern "C" int ryolo_nchw_to_padded(const float* src, int batch, int c, int h, i
   const size_t total = (size_t)batch * ((c + 7) / 8) * h * w;
   nchw_to_padded_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, batch, c, h, w,
                                                                             static_cast<__nv_bfloat16*>(dst), dst_cstride);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_head_grad_to_padded(const float* g, int batch, int na, int no, int ny, int nx, void* dst,
+                                         int dst_cstride, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(g && dst && batch > 0 && na > 0 && no > 0 && ny > 0 && nx > 0);
+  RYOLO_ARG_CHECK(dst_cstride >= na * no && dst_cstride % 8 == 0 && batch <= 65535 && ny <= 65535);
+  const int cpad = (na * no + 7) & ~7;
+  const size_t smem = (size_t)32 * cpad * 2;
+  RYOLO_ARG_CHECK(smem <= 160 * 1024);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    RYOLO_CUDA_TRY(cudaFuncSetAttribute(head_grad_to_padded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((unsigned)((nx + 31) / 32), (unsigned)ny, (unsigned)batch);
+  head_grad_to_padded_kernel<<<grid, 256, smem, stream>>>(g, na, no, ny, nx, static_cast<__nv_bfloat16*>(dst), dst_cstride);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }

@@ -264,10 +264,12 @@ class TrainPlan:
         pgrads = {}
         for blk, g, yi in zip(self.heads, grads, m.yolo_layers):
             layer = m.module_list[yi]
-            g_nchw = g.permute(0, 1, 4, 2, 3).reshape(self.batch, blk.cout, blk.oh, blk.ow).contiguous().float()
-            pgrads[(blk.i, "Conv2d.bias")] = g_nchw.sum((0, 2, 3))
-            _lib.check(lib.ryolo_nchw_to_padded(_lib.ptr(g_nchw), self.batch, blk.cout, blk.oh, blk.ow, _lib.ptr(blk.dz),
-                                                blk.zcs, st), "nchw_to_padded")
+            # g: [B, na, ny, nx, no] fp32 as autograd delivers it; filter index of the head conv = a * no + k
+            g = g.contiguous().float()
+            na, no = g.shape[1], g.shape[4]
+            pgrads[(blk.i, "Conv2d.bias")] = g.sum((0, 2, 3)).reshape(-1)
+            _lib.check(lib.ryolo_head_grad_to_padded(_lib.ptr(g), self.batch, na, no, blk.oh, blk.ow, _lib.ptr(blk.dz),
+                                                     blk.zcs, st), "head_grad_to_padded")
         for blk in reversed(self.blocks):
             seq = m.module_list[blk.i]
             if blk.is_head:

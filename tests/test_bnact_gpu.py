@@ -115,3 +115,26 @@ def test_dgrad_via_forward_kernel_vs_autograd(cin, cout, k, stride, h, w):
     want = x.grad + prior
     sc = float(want.abs().max())
     assert float((got - want).abs().max()) <= 2.0 ** -7 * sc, (float((got - want).abs().max()), sc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 3, 7, 5, 9), (3, 72, 7, 19, 19), (1, 4, 6, 40, 33)])
+def test_head_grad_to_padded(shape):
+    """autograd's head gradient [B, na, ny, nx, no] fp32 -> bf16 padded NHWC with channel = a*no + k (exact bf16 rounding
+    of the same values as the permute + nchw_to_padded path); channels beyond na*no and the halo stay untouched"""
+    import rotate_yolov3_b200 as pkg
+    from rotate_yolov3_b200 import layout as L
+    dev = torch.device("cuda")
+    b, na, no, ny, nx = shape
+    g = torch.randn(b, na, ny, nx, no, generator=torch.Generator().manual_seed(7)).to(dev)
+    c = na * no
+    cs = L.round_up(c, 32)
+    dst = L.alloc_padded(b, ny, nx, cs, dev)
+    dst[..., c:] = 3.0
+    st = pkg._lib.lib.ryolo_head_grad_to_padded(pkg._lib.ptr(g), b, na, no, ny, nx, pkg._lib.ptr(dst), cs,
+                                                pkg._lib.stream_ptr(dev))
+    assert st == 0, pkg._lib.last_error()
+    want = g.permute(0, 2, 3, 1, 4).reshape(b, ny, nx, c).to(torch.bfloat16)
+    assert torch.equal(dst[:, 1:-1, 1:-1, :c], want)
+    assert float((dst[:, 1:-1, 1:-1, c:] - 3.0).abs().max() if cs > c else 0.0) == 0.0
+    assert float(dst[:, 0, :, :c].abs().max()) == 0 and float(dst[:, :, 0, :c].abs().max()) == 0
