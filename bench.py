@@ -35,6 +35,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+WORKLOADS = {   # config.workload of both arms (ours / --impl reference)
+    "riou": "rotated IoU, N=M=10000 random (cx,cy,w,h,theta) boxes on a 608^2 canvas (BASELINE configs[1])",
+    "rnms": "rotated NMS, 20000 boxes/image, 1 class, IoU thr 0.5 (BASELINE configs[2])",
+    "train": "Darknet-53 (cfg/yolov3.cfg graph) training step: fwd (batch-stat BN) + compute_loss + bwd + SGD, "
+             "608x608 synthetic (BASELINE configs[3])",
+    "detect": "detect e2e: Darknet-53 (cfg/yolov3.cfg graph) eval forward + YOLO decode + conf filter + top-20000 + "
+              "rotated NMS thr 0.5, 608x608 (BASELINE configs[4] shape)",
+}
+
+
 class ClockSampler:
     """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled from a thread
     every 2 ms (an `nvidia-smi -lms` child needs ~0.3 s to produce its first line -- longer than most timed regions
@@ -283,20 +293,21 @@ def main():
             return
         if args.workload == "riou":
             cb, times = cpu_riou(sample_rows=10000, steps=max(1, min(K, 3)) + min(W, 1))
-            workload = "rotated IoU 10k x 10k (config 2), the full 1e8 pairs per step"
+            sample = "the full 1e8 pairs per step"
         elif args.workload == "rnms":
             cb, times = cpu_rnms(20000, steps=max(1, min(K, 2)))
-            workload = "rotated NMS (config 3), the full 20000 boxes per step"
+            sample = "the full 20000 boxes per step"
         elif args.workload == "train":
             cb, times = cpu_train(steps=max(1, min(K, 2)), batch=2)
-            workload = "Darknet-53 training step (config 4), bounded sample of 2 images per step"
+            sample = "bounded sample of 2 images per step (stock PyTorch CPU kernels on the same graph)"
         else:
             print(json.dumps({"impl": "reference", "unavailable": "detect workload has no CPU reference arm yet"}))
             return
         print(json.dumps({"impl": "reference", "metric": metric[0], "value": cb["value"], "unit": metric[1],
                           "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * min(times),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": WORKLOADS[args.workload], "sample": sample},
                           "cpu_baseline": cb,
                           "e2e": {"value": cb["value"], "unit": metric[1], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -340,7 +351,7 @@ def main():
             out_h.copy_(outs[i & 1], non_blocking=True)
             torch.cuda.current_stream().synchronize()
         h2d, d2h = (n + m) * 5 * 4, n * m * 4
-        cfg = {"workload": "rotated IoU, N=M=10000 random (cx,cy,w,h,theta) boxes on a 608^2 canvas (BASELINE configs[1])",
+        cfg = {"workload": WORKLOADS["riou"],
                "mode": "iou", "sharding": "row blocks of A per rank, B replicated, no collective",
                "l2": "each step streams a 400 MB output (> 126 MB L2) into alternating buffers"}
         scale = 1e-6
@@ -363,7 +374,7 @@ def main():
             k = pkg.r_nms(dd, 0.5)
             keep_h[:len(k)].copy_(k)
         h2d, d2h = n * 6 * 4, 8 * 8666
-        cfg = {"workload": "rotated NMS, 20000 boxes/image, 1 class, IoU thr 0.5 (BASELINE configs[2])",
+        cfg = {"workload": WORKLOADS["rnms"],
                "sharding": "one image per rank (replicas), no collective",
                "l2": "50 MB mask rewritten every step; 192 MB flush buffer written between timed steps"}
         scale = 1.0
@@ -419,11 +430,10 @@ def main():
             loss_h.copy_(loss.detach(), non_blocking=True)
             torch.cuda.current_stream().synchronize()
         h2d, d2h = per_gpu * 3 * 608 * 608 * 4 + tg_h.numel() * 4, 4
-        cfg = {"workload": "Darknet-53 (cfg/yolov3.cfg graph) training step: fwd (batch-stat BN) + compute_loss + bwd + SGD, "
-                           "608x608 synthetic (BASELINE configs[3])",
+        cfg = {"workload": WORKLOADS["train"],
                "global_batch": per_gpu * world, "per_gpu_batch": per_gpu, "precision": "bf16 operands/activations, fp32 "
                "accumulate and parameter gradients", "parallelism": "dp%d" % world,
-               "collective": "one NCCL all-reduce of 62.4M fp32 gradients per step (after backward, not yet overlapped)",
+               "collective": "one flat NCCL all-reduce of 62.4M fp32 gradients per step (after backward, not overlapped)",
                "l2": "activations of one step (tens of GB) exceed the 126 MB L2"}
         scale = 1.0
     else:
@@ -486,8 +496,7 @@ def main():
             counts_h.copy_(counts, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         h2d, d2h = per_gpu * 3 * 608 * 608 * 4, per_gpu * 4
-        cfg = {"workload": "detect e2e: Darknet-53 (cfg/yolov3.cfg graph) eval forward + YOLO decode + conf filter + top-20000 + "
-                           "rotated NMS thr 0.5, 608x608 (BASELINE configs[4] shape)",
+        cfg = {"workload": WORKLOADS["detect"],
                "global_batch": per_gpu * world, "per_gpu_batch": per_gpu, "precision": "bf16 operands, fp32 accumulate",
                "sharding": "images per rank, no collective",
                "l2": "activations of one forward (~8 GB at batch 32) exceed the 126 MB L2"}
