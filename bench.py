@@ -623,6 +623,21 @@ def main():
     roof = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["src"] + " (burst copy)",
             "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms}
+    if args.workload == "riou":
+        # SURVEY.md 8d config 2 also asks for the measured non-zero fraction and the fp32 issue rate: the kernel is bound
+        # by instruction issue, not by the 400 MB it writes
+        roof["nonzero_fraction"] = float(torch.count_nonzero(outs[0]).item()) / float(n * m)
+        if os.path.exists(tp):
+            ti = json.load(open(tp)).get("thread_instr_per_launch")
+            if ti:
+                lane_rate = ti / (kern_ms * 1e-3)
+                lane_peak = 148 * 128 * 1.965e9           # fp32 lanes x boost clock
+                roof["lane_ops_per_s"] = lane_rate
+                roof["lane_ops_frac_of_issue_peak"] = lane_rate / lane_peak
+    else:
+        kept = pkg.r_nms(d, 0.5)
+        roof["kept"] = int(len(kept))
+        roof["iou_evals_per_s_upper_triangle"] = 0.5 * n * (n - 1) / (kern_ms * 1e-3)
 
     out = {"metric": metric[0], "value": value, "unit": metric[1], "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
