@@ -379,6 +379,9 @@ class Darknet(nn.Module):
                     self._tplan_key = key
                 return list(DarknetTrainFn.apply(self._tplan, x, *list(self.parameters())))
         with torch.cuda.device(x.device):
+            # the plan holds PACKED (BN-folded, bf16) copies of the weights: rebuild it when any parameter or buffer was
+            # modified in place since (optimizer step, manual edits); train()/eval()/load_state_dict drop it explicitly
+            key = key + (sum(t._version for t in self.parameters()) + sum(t._version for t in self.buffers()),)
             if self._plan is None or self._plan_key != key:
                 self._plan = self._build_plan(b, h, w, x.device)
                 self._plan_key = key
@@ -398,41 +401,40 @@ class Darknet(nn.Module):
             return self._run_eval(x, b, h, w)
 
     def _run_eval(self, x, b, h, w):
-        if True:
-            plan = self._plan
-            lib = _lib.lib
-            stream = _lib.stream_ptr(x.device)
-            for kind, a in plan["steps"]:
-                if kind == "maxpool":
-                    st = lib.ryolo_maxpool2x2(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"], a["stride"],
-                                              ctypes.c_void_p(a["y"]), a["ycs"], stream)
-                    _lib.check(st, "ryolo_maxpool2x2")
-                elif kind == "s2d":
-                    st = lib.ryolo_space_to_depth(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"],
-                                                  _lib.ptr(a["xs"]), a["xs"].shape[-1], stream)
-                    _lib.check(st, "ryolo_space_to_depth")
-                elif kind == "first":
-                    if a["xs"] is not None:
-                        st = lib.ryolo_conv_first_s2d_fwd(_lib.ptr(x), b, h, w, _lib.ptr(a["w"]), _lib.ptr(a["b"]),
-                                                          a["cout"], a["slope"], _lib.ptr(a["xs"]), a["xs"].shape[-1], stream)
-                    else:
-                        v = a["out"]
-                        st = lib.ryolo_conv_first_fwd(_lib.ptr(x), b, h, w, _lib.ptr(a["w"]), _lib.ptr(a["b"]), a["cout"],
-                                                      a["slope"], ctypes.c_void_p(v.ptr), v.cs, stream)
-                    _lib.check(st, "ryolo_conv_first_fwd")
+        plan = self._plan
+        lib = _lib.lib
+        stream = _lib.stream_ptr(x.device)
+        for kind, a in plan["steps"]:
+            if kind == "maxpool":
+                st = lib.ryolo_maxpool2x2(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"], a["stride"],
+                                          ctypes.c_void_p(a["y"]), a["ycs"], stream)
+                _lib.check(st, "ryolo_maxpool2x2")
+            elif kind == "s2d":
+                st = lib.ryolo_space_to_depth(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"],
+                                              _lib.ptr(a["xs"]), a["xs"].shape[-1], stream)
+                _lib.check(st, "ryolo_space_to_depth")
+            elif kind == "first":
+                if a["xs"] is not None:
+                    st = lib.ryolo_conv_first_s2d_fwd(_lib.ptr(x), b, h, w, _lib.ptr(a["w"]), _lib.ptr(a["b"]),
+                                                      a["cout"], a["slope"], _lib.ptr(a["xs"]), a["xs"].shape[-1], stream)
                 else:
-                    st = lib.ryolo_conv_bn_act_fwd(ctypes.byref(a["desc"]), ctypes.c_void_p(a["x"]), _lib.ptr(a["w"]),
-                                                   _lib.ptr(a["b"]), ctypes.c_void_p(a["r"]) if a["r"] else None,
-                                                   ctypes.c_void_p(a["y"]), None, 0, stream)
-                    _lib.check(st, "ryolo_conv_bn_act_fwd")
-            if not self.yolo_layers:      # trunk graph without YOLO layers: the raw head maps [B, filters, ny, nx]
-                return [head for _, head in plan["heads"]]
-            nc = self.module_list[self.yolo_layers[0]].nc
-            total = sum(plan["rows"])
-            io = torch.empty((b, total, nc + 6), dtype=torch.float32, device=x.device)
-            ps = []
-            off = 0
-            for (ci, head), yi, r in zip(plan["heads"], self.yolo_layers, plan["rows"]):
-                ps.append(self.module_list[yi].decode_into(head, (h, w), io, total, off))
-                off += r
+                    v = a["out"]
+                    st = lib.ryolo_conv_first_fwd(_lib.ptr(x), b, h, w, _lib.ptr(a["w"]), _lib.ptr(a["b"]), a["cout"],
+                                                  a["slope"], ctypes.c_void_p(v.ptr), v.cs, stream)
+                _lib.check(st, "ryolo_conv_first_fwd")
+            else:
+                st = lib.ryolo_conv_bn_act_fwd(ctypes.byref(a["desc"]), ctypes.c_void_p(a["x"]), _lib.ptr(a["w"]),
+                                               _lib.ptr(a["b"]), ctypes.c_void_p(a["r"]) if a["r"] else None,
+                                               ctypes.c_void_p(a["y"]), None, 0, stream)
+                _lib.check(st, "ryolo_conv_bn_act_fwd")
+        if not self.yolo_layers:      # trunk graph without YOLO layers: the raw head maps [B, filters, ny, nx]
+            return [head for _, head in plan["heads"]]
+        nc = self.module_list[self.yolo_layers[0]].nc
+        total = sum(plan["rows"])
+        io = torch.empty((b, total, nc + 6), dtype=torch.float32, device=x.device)
+        ps = []
+        off = 0
+        for (ci, head), yi, r in zip(plan["heads"], self.yolo_layers, plan["rows"]):
+            ps.append(self.module_list[yi].decode_into(head, (h, w), io, total, off))
+            off += r
         return io, tuple(ps)

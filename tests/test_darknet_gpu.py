@@ -114,3 +114,22 @@ def test_boundary_and_state_dict_names():
     assert io1.shape == (1, 2 * (4 + 16 + 64), 7) and io2.shape == (3, 2 * (6 + 24 + 96), 7)
     yl = m.module_list[106]
     assert (yl.nx, yl.ny) == (8, 12) and float(yl.stride) == 8.0 and yl.anchor_vec.shape == (2, 3)
+
+
+def test_eval_plan_follows_in_place_weight_updates():
+    """the eval plan caches packed, BN-folded weights; an in-place parameter update (optimizer step, manual edit) must
+    invalidate it"""
+    import rotate_yolov3_b200 as pkg
+    from helpers import init_darknet_weights, mini_cfg
+    dev = torch.device("cuda")
+    m = pkg.Darknet(mini_cfg(), {"context_factor": 1.0})
+    init_darknet_weights(m, seed=3)
+    m = m.to(dev).eval()
+    x = torch.rand(2, 3, 64, 96, device=dev)
+    with torch.no_grad():
+        io0 = m(x)[0].clone()
+        io1 = m(x)[0].clone()
+        assert torch.equal(io0, io1)
+        m.module_list[0].Conv2d.weight.mul_(1.5)          # in place, still in eval mode
+        io2 = m(x)[0].clone()
+    assert not torch.allclose(io0, io2)
