@@ -165,6 +165,7 @@ class Darknet(nn.Module):
         self.seen = np.array([0], dtype=np.int64)
         self._plan = None
         self._plan_key = None
+        self._ver_tensors = None
         self._tplan = None
         self._tplan_key = None
         # opt-in: replay the eval forward as ONE CUDA graph (78 launches -> 1).  The returned tensors are then static
@@ -188,6 +189,13 @@ class Darknet(nn.Module):
         self._plan = None
         self._graph = None
         return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):      # .to() / .cuda() / .half() / .float(): storage changes without a version bump
+        self._plan = None
+        self._graph = None
+        self._tplan = None
+        self._ver_tensors = None
+        return super()._apply(fn, *a, **k)
 
     # ------------------------------------------------------------------------------------------------------
     def _folded(self, i, device):
@@ -381,7 +389,9 @@ class Darknet(nn.Module):
         with torch.cuda.device(x.device):
             # the plan holds PACKED (BN-folded, bf16) copies of the weights: rebuild it when any parameter or buffer was
             # modified in place since (optimizer step, manual edits); train()/eval()/load_state_dict drop it explicitly
-            key = key + (sum(t._version for t in self.parameters()) + sum(t._version for t in self.buffers()),)
+            if self._ver_tensors is None:      # walking the module tree costs ~1 ms; the tensor objects are stable
+                self._ver_tensors = list(self.parameters()) + list(self.buffers())
+            key = key + (sum(t._version for t in self._ver_tensors),)
             if self._plan is None or self._plan_key != key:
                 self._plan = self._build_plan(b, h, w, x.device)
                 self._plan_key = key
