@@ -95,3 +95,33 @@ def test_masked_loss_equals_indexed_loss():
         assert torch.allclose(i0, i1, rtol=1e-5, atol=1e-6)
         for a, b in zip(g0, g1):
             assert torch.allclose(a, b, rtol=1e-4, atol=1e-7)
+
+
+def test_masked_assignment_selects_the_rows_build_targets_keeps():
+    """_targets_masked (fixed shapes + mask, vectorised orphan rescue) marks exactly the (layer, anchor, target) rows that
+    build_targets returns after its data-dependent filtering -- same indices, boxes and anchors, in the same order"""
+    from rotate_yolov3_b200.loss import _targets_masked, build_targets
+    g = np.load(os.path.join(GOLDEN, "loss_golden.npz"))
+    hyp = {str(k): float(v) for k, v in zip(g["hyp_keys"], g["hyp_vals"])}
+    ps = [torch.from_numpy(g["p%d" % k]) for k in range(3)]
+    m = _fake_model(ps, hyp)
+    gen = torch.Generator().manual_seed(11)
+    for nt in (1, 5, 64):
+        t = torch.rand(nt, 7, generator=gen)
+        t[:, 0] = torch.randint(0, 2, (nt,), generator=gen).float()
+        t[:, 1] = 0.0
+        t[:, 2:4] = t[:, 2:4] * 0.98 + 0.01
+        t[:, 4:6] = t[:, 4:6] * 0.5 + 0.002        # many orphans (tiny boxes) and many multi-anchor matches
+        t[:, 6] = (t[:, 6] - 0.5) * 3.1
+        if nt > 2:
+            t[1] = t[0]                              # exact duplicates: identical IoUs for two targets
+        tcls, tbox, indices, av = build_targets(m, t.clone(), hyp)
+        rows = _targets_masked(m, t.clone(), hyp)
+        for lid, r in enumerate(rows):
+            k = r["mask"].nonzero().view(-1)
+            assert len(k) == len(tcls[lid])
+            assert torch.equal(r["tcls"][k], tcls[lid])
+            assert torch.equal(r["tbox"][k], tbox[lid])
+            assert torch.equal(r["av"][k], av[lid])
+            for name, ref in zip(("b", "a", "gj", "gi"), indices[lid]):
+                assert torch.equal(r[name][k], ref)
