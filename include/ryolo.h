@@ -276,6 +276,70 @@ int ryolo_head_grad_to_padded(const float* g, int batch, int na, int no, int ny,
  * (27 real, column = c*9 + kh*3 + kw), so that the first layer runs on the same GEMM kernels. */
 int ryolo_im2col_first(const float* img, int batch, int h, int w, void* dst, void* stream);
 
+/* ------------------------------------------------------------------------------------------ *
+ * Parity-precision path (Darknet(..., precision="parity")): fp32-grade conv blocks on the bf16
+ * tensor pipe, for the 1e-4 tolerance north_star states against the reference's fp32 nn.Conv2d
+ * (model/models.py:55-65).  GEMM operands are SPLIT bf16 tensors: padded NHWC like above, but
+ * every value v is two planes hi = bf16(v), lo = bf16(v - hi), `lo` channels apart in the same
+ * row ("split view": pointer to channel 0 of plane 0, channel stride, plane offset `lo`, number of
+ * planes: plane k = bf16 of the remainder left by planes < k, k*lo channels further; three planes
+ * carry all 24 bits of an fp32).  Conv results, BN / PReLU / shortcut arithmetic and all gradients
+ * of activations are fp32 padded NHWC; reductions are fp64.  a*w is evaluated as a sum of TERMS
+ * a_i*w_j (a term table, 2 bits per term per operand: i + j <= 2 for three planes), exact products;
+ * the TMEM accumulator is drained every 8 k-steps into round-to-nearest fp32 register sums (the tensor
+ * pipe's own accumulator truncates).
+ * ------------------------------------------------------------------------------------------ */
+/* weight [cout,cin,k,k] fp32 -> bf16 [k*k][round_up(cout,64)][nterms*round_up(cin,64)]; term t of the
+ * K range holds plane (w_plane_code >> 2t) & 3.  mode as ryolo_conv_pack_weights_ex
+ * (ksize 2 / -2 for the space-to-depth forms; cout/cin are those of the PACKED operand). */
+size_t ryolo_px_packed_weight_bytes(int cout, int cin, int ksize, int nterms);
+int ryolo_px_pack_weights(const float* weight, int cout, int cin, int ksize, int nterms,
+                          int w_plane_code, int mode, void* packed_out, void* stream);
+/* out[p, co] (+)= sum over terms, taps, channels.  x_base: start of the split buffer row 0, the view
+ * starts x_ch_off channels in; (a_plane_code >> 2t) & 3 is the activation plane of term t.  out: fp32
+ * padded NHWC on the same grid (stride 1; stride-2 convs run on space-to-depth inputs), columns
+ * [0, out_cols) written, accumulate != 0 adds to the existing contents (dgrad). */
+int ryolo_px_conv(const void* x_base, int x_cstride, int x_ch_off, int plane_stride, int cin,
+                  const void* packed_w, int nterms, int a_plane_code, int batch, int in_h, int in_w,
+                  int ksize, int cout, float* out, int out_cstride, int out_cols, int accumulate,
+                  void* stream);
+/* wgrad of split operands = ryolo_conv_wgrad over all planes of dz and x ([taps][np*plane_out][np*plane_in]);
+ * this sums the nplanes^2 plane blocks into nn.Conv2d layout (mode 0 / 2 as ryolo_conv_unpack_wgrad); cin_off:
+ * first channel of x's view inside its plane (a conv reading a slice of a concat buffer). */
+int ryolo_px_unpack_wgrad(const float* dw, int plane_out, int plane_in, int nplanes, int mode, int cout,
+                          int cin, int ksize, int cin_off, float* grad, void* stream);
+/* batch statistics of fp32 z: sums[0..c) = sum, [c..2c) = sum of squares (fp64, zeroed inside) */
+int ryolo_px_bn_stats(const float* z, int z_cstride, int batch, int h, int w, int c, double* sums,
+                      void* stream);
+/* eval_mode 0: batch statistics from sums (running statistics updated); 1: running statistics. */
+int ryolo_px_bn_finalize(const double* sums, int c, double count, float eps, float momentum,
+                         const float* gamma, const float* beta, int eval_mode, float* mean,
+                         float* invstd, float* scale, float* shift, float* running_mean,
+                         float* running_var, void* stream);
+/* y = prelu(z*scale + shift) [+ residual] -> split view (slope_dev NULL: linear) */
+int ryolo_px_bn_act_fwd(const float* z, int z_cstride, int batch, int h, int w, int c,
+                        const float* scale, const float* shift, const float* slope_dev,
+                        const void* residual, int res_cstride, int res_lo, void* y, int y_cstride,
+                        int y_lo, int upsample2x, int nplanes, void* stream);
+/* backward: dy fp32 (2h x 2w when upsample2x), z fp32 -> sums fp64 [2c+1] (d beta, d gamma, d slope),
+ * dz split view, shortcut gradient gres fp32 (+)= dy. */
+int ryolo_px_bn_act_bwd(const float* dy, int dy_cstride, int upsample2x, const float* z, int z_cstride,
+                        int batch, int h, int w, int c, const float* scale, const float* shift,
+                        const float* mean, const float* invstd, const float* slope_dev,
+                        int batch_stats, double* sums, void* dz, int dz_cstride, int dz_lo, float* gres,
+                        int gres_cstride, int gres_accumulate, int nplanes, void* stream);
+int ryolo_px_im2col_first(const float* img, int batch, int h, int w, void* dst, int dst_cstride,
+                          int dst_lo, int nplanes, void* stream);
+/* fp32 padded NHWC (+ bias[c]) -> fp32 NCHW [B,c,h,w] (the linear heads feeding ryolo_yolo_decode) */
+int ryolo_px_to_nchw(const float* z, int z_cstride, int batch, int c, int h, int w, const float* bias,
+                     float* out, void* stream);
+int ryolo_px_head_grad(const float* g, int batch, int na, int no, int ny, int nx, void* dst,
+                       int dst_cstride, int dst_lo, int nplanes, void* stream);
+int ryolo_px_depth_to_space(const float* dxs, int dxs_cstride, int batch, int h, int w, int c, float* gx,
+                            int gx_cstride, int accumulate, void* stream);
+int ryolo_px_split_from_nchw(const float* src, int batch, int c, int h, int w, void* dst,
+                             int dst_cstride, int dst_lo, int nplanes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

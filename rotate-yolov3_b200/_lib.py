@@ -22,7 +22,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = ctypes.CDLL(LIB_PATH)
 
-_vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_vp, _i, _f, _sz, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_double
 
 
 class ConvDesc(ctypes.Structure):
@@ -68,6 +68,20 @@ SIGNATURES = {
     "ryolo_maxpool2x2": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "ryolo_nchw_to_padded": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "ryolo_im2col_first": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "ryolo_px_packed_weight_bytes": (_sz, [_i, _i, _i, _i]),
+    "ryolo_px_pack_weights": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ryolo_px_conv": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "ryolo_px_unpack_wgrad": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ryolo_px_bn_stats": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ryolo_px_bn_finalize": (_i, [_vp, _i, _d, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ryolo_px_bn_act_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+    "ryolo_px_bn_act_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i,
+                                 _vp, _i, _i, _i, _vp]),
+    "ryolo_px_im2col_first": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "ryolo_px_to_nchw": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ryolo_px_head_grad": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "ryolo_px_depth_to_space": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "ryolo_px_split_from_nchw": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)

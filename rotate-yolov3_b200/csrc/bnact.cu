@@ -636,11 +636,7 @@ extern "C" int ryolo_head_grad_to_padded(const float* g, int batch, int na, int 
   const int cpad = (na * no + 7) & ~7;
   const size_t smem = (size_t)32 * cpad * 2;
   RYOLO_ARG_CHECK(smem <= 160 * 1024);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    RYOLO_CUDA_TRY(cudaFuncSetAttribute(head_grad_to_padded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  RYOLO_SMEM_OPT_IN(head_grad_to_padded_kernel, 160 * 1024);   // upper bound checked above; per device
   dim3 grid((unsigned)((nx + 31) / 32), (unsigned)ny, (unsigned)batch);
   head_grad_to_padded_kernel<<<grid, 256, smem, stream>>>(g, na, no, ny, nx, static_cast<__nv_bfloat16*>(dst), dst_cstride);
   RYOLO_LAUNCH_CHECK();

@@ -46,6 +46,36 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     }                                                                           \
   } while (0)
 
+
+// Per-device one-time setup.  Opt-in shared-memory sizes and SM counts are properties of a DEVICE: a process that
+// uses several GPUs (model.to("cuda:1"), multi-device tests) must set / query them once per device, not once per
+// process.  Racing threads may both run the (idempotent) setup; nobody launches before it has run on their device.
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+inline int device_sm_count() {
+  static std::atomic<int> cache[64];
+  const int d = current_device() & 63;
+  int n = cache[d].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+    if (n <= 0) n = 148;
+    cache[d].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+#define RYOLO_SMEM_OPT_IN(kernel, bytes)                                                                      \
+  do {                                                                                                        \
+    static std::atomic<uint64_t> _mask{0};                                                                    \
+    const uint64_t _bit = 1ull << (::ryolo::current_device() & 63);                                           \
+    if (!(_mask.load(std::memory_order_acquire) & _bit)) {                                                    \
+      RYOLO_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _mask.fetch_or(_bit, std::memory_order_release);                                                        \
+    }                                                                                                         \
+  } while (0)
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // bump allocator over a caller-owned workspace

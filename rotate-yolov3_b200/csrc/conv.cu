@@ -36,6 +36,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "pack.cuh"
 #include "tc05.cuh"
 
 namespace ryolo {
@@ -460,12 +461,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: [cout, cin, k, k] fp32 (* per-filter scale) -> bf16 [k*k][cout_pad][cin_pad], zero padded
 // ---------------------------------------------------------------------------------------------------------------
-// mode 0: plain            packed[tap][co][ci] = w[co][ci][kh][kw] (* scale[co])
-// mode 1: dgrad of mode 0  packed[tap][co][ci] = w[ci][co][k-1-kh][k-1-kw]      (w = the FORWARD weight [cin_d, cout_d, k, k])
-// mode 2: space-to-depth   packed[(qy,qx)][co][(py*2+px)*C + c] = w[co][c][kh(qy,py)][kw(qx,px)] or 0   (w = [cout, C, 3, 3])
-// mode 3: dgrad of mode 2  packed[(ty,tx)][(py*2+px)*C + c][ci] = w[ci][c][kh(1-ty,py)][kw(1-tx,px)] or 0
-__device__ __forceinline__ int s2d_k(int q, int p) { return q == 0 ? (p == 1 ? 0 : -1) : (p == 0 ? 1 : 2); }
-
+// modes: see pack.cuh
 __global__ void conv_pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ scale, int cout, int cin,
                                          int ks, int cout_pad, int cin_pad, int mode, __nv_bfloat16* __restrict__ out) {
   const size_t total = (size_t)ks * ks * cout_pad * cin_pad;
@@ -475,20 +471,7 @@ __global__ void conv_pack_weights_kernel(const float* __restrict__ w, const floa
     const int tap = (int)(i / ((size_t)cin_pad * cout_pad));
     float v = 0.f;
     if (ci < cin && co < cout) {
-      const int ty = tap / ks, tx = tap % ks;
-      if (mode == 0) {
-        v = w[(((size_t)co * cin + ci) * ks + ty) * ks + tx];
-      } else if (mode == 1) {
-        v = w[(((size_t)ci * cout + co) * ks + (ks - 1 - ty)) * ks + (ks - 1 - tx)];
-      } else if (mode == 2) {
-        const int C = cin >> 2, ph = ci / C, c = ci - ph * C;
-        const int kh = s2d_k(ty, ph >> 1), kw = s2d_k(tx, ph & 1);
-        if (kh >= 0 && kw >= 0) v = w[(((size_t)co * C + c) * 3 + kh) * 3 + kw];
-      } else {
-        const int C = cout >> 2, ph = co / C, c = co - ph * C;
-        const int kh = s2d_k(1 - ty, ph >> 1), kw = s2d_k(1 - tx, ph & 1);
-        if (kh >= 0 && kw >= 0) v = w[(((size_t)ci * C + c) * 3 + kh) * 3 + kw];
-      }
+      v = pack_value(w, cout, cin, ks, mode, tap, co, ci);
       if (scale && (mode == 0 || mode == 2)) v *= scale[co];
     }
     out[i] = __float2bfloat16_rn(v);
@@ -574,17 +557,8 @@ template <int BN, int NBUF>
 static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
                        const ConvParams& p, cudaStream_t stream) {
   using S = ConvSmem<BN, NBUF>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RYOLO_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    RYOLO_CUDA_TRY(cudaGetDevice(&dev));
-    RYOLO_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  RYOLO_SMEM_OPT_IN((conv_igemm_kernel<BN, NBUF>), S::kTotal);
+  const int num_sms = device_sm_count();
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   conv_igemm_kernel<BN, NBUF><<<grid, CONV_THREADS, S::kTotal, stream>>>(ma, mb, mo, mr, p);

@@ -182,16 +182,8 @@ __global__ void __launch_bounds__(FIRST_THREADS) conv_first_tc_kernel(const floa
 template <int COUT, bool S2D>
 static int launch_first(const float* img, int batch, int h, int w, const float* weight, const float* bias, float slope,
                         void* y, int cs, cudaStream_t stream) {
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
-    RYOLO_CUDA_TRY(cudaFuncSetAttribute(conv_first_tc_kernel<COUT, S2D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        FirstSmem::kTotal));
-    int dev = 0;
-    RYOLO_CUDA_TRY(cudaGetDevice(&dev));
-    RYOLO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  RYOLO_SMEM_OPT_IN((conv_first_tc_kernel<COUT, S2D>), FirstSmem::kTotal);
+  const int sms = device_sm_count();
   const size_t npix = (size_t)batch * h * w;
   const long long ntiles = (long long)((npix + 127) / 128);
   RYOLO_ARG_CHECK(ntiles < (1ll << 31));

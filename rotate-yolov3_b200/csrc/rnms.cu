@@ -504,12 +504,7 @@ static int rnms_impl(const float* dets, int n, float thr, int64_t* keep_out, int
                                                             p.geom, p.keep_flag);
   RYOLO_LAUNCH_CHECK();
   {
-    static bool attr_set = false;
-    if (!attr_set) {
-      RYOLO_CUDA_TRY(cudaFuncSetAttribute(rnms_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(MaskSmem)));
-      attr_set = true;
-    }
+    RYOLO_SMEM_OPT_IN(rnms_mask_kernel, sizeof(MaskSmem));
     const size_t smem = (size_t)p.col_blocks * sizeof(u64) * 2;
     if (smem > 200 * 1024) {
       set_err("ryolo_rnms: n=%d too large for the single-CTA scan (col_blocks=%d)", n, p.col_blocks);

@@ -177,11 +177,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_const
 template <int BN, int TG>
 static int launch_wgrad(const CUtensorMap& mdz, const CUtensorMap& mx, const WgradParams& p, cudaStream_t stream) {
   using C = WgradCfg<BN, TG>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RYOLO_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel<BN, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    attr_set = true;
-  }
+  RYOLO_SMEM_OPT_IN((conv_wgrad_kernel<BN, TG>), C::kSmem);
   const int grid = p.tap_groups * p.m_tiles * p.n_tiles * p.ksplit;
   conv_wgrad_kernel<BN, TG><<<grid, WG_THREADS, C::kSmem, stream>>>(mdz, mx, p);
   RYOLO_LAUNCH_CHECK();
@@ -212,12 +208,7 @@ extern "C" int ryolo_conv_wgrad(const void* dz, int dz_cstride, int cout_pad, co
   p.m_tiles = (cout_pad + WG_BM - 1) / WG_BM;
   p.n_tiles = (cin_pad + bn - 1) / bn;
   p.ksteps_total = (p.np + WG_BK - 1) / WG_BK;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    RYOLO_CUDA_TRY(cudaGetDevice(&dev));
-    RYOLO_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = device_sm_count();
   // taps per CTA: the kernel row (3 or 2 taps) when the accumulators fit TMEM and the layer is thin enough to be
   // operand-stream bound; RYOLO_WGRAD_TG=1 forces one tap per CTA (measurement knob)
   static int force_tg = -1;

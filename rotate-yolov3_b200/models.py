@@ -153,8 +153,15 @@ class _View:
 
 
 class Darknet(nn.Module):
-    def __init__(self, cfg, hyp, arc="default"):
+    def __init__(self, cfg, hyp, arc="default", precision="bf16"):
+        """precision: "bf16" = throughput mode (bf16 operands / activations, fp32 accumulate); "parity" = fp32-grade
+        arithmetic on the same tensor pipe (split bf16 operands, parity_path.py) for the reference's 1e-4 tolerance."""
         super().__init__()
+        if precision not in ("bf16", "parity"):
+            raise ValueError("precision must be 'bf16' or 'parity'")
+        self.precision = precision
+        self._pplan = None
+        self._pplan_key = None
         self.module_defs = parse_model_cfg(cfg)
         self.net_hyper = self.module_defs[0]
         self.module_list, self.routes = create_modules(self.module_defs, arc, hyp)
@@ -194,6 +201,7 @@ class Darknet(nn.Module):
         self._plan = None
         self._graph = None
         self._tplan = None
+        self._pplan = None
         self._ver_tensors = None
         return super()._apply(fn, *a, **k)
 
@@ -378,6 +386,21 @@ class Darknet(nn.Module):
         x = x.float().contiguous()
         b, _, h, w = x.shape
         key = (b, h, w, x.device)
+        if self.precision == "parity":
+            from .parity_path import DarknetParityFn, ParityPlan
+            with torch.cuda.device(x.device):
+                pkey = key + (self.training,)
+                if self._pplan is None or self._pplan_key != pkey:
+                    self._pplan = ParityPlan(self, b, h, w, x.device, self.training)
+                    self._pplan_key = pkey
+                if self.training:
+                    names = [n for n, _ in self.named_parameters()]
+                    return list(DarknetParityFn.apply(self._pplan, x, names, *list(self.parameters())))
+                with torch.no_grad():
+                    heads = self._pplan.forward(x)
+                    if not self.yolo_layers:
+                        return [hd.clone() for hd in heads]
+                    return self._decode_heads(heads, b, h, w, x.device)
         if self.training:
             # reference models.py:192-194, 290-292: list of raw [B, na, ny, nx, nc+6] tensors; differentiable
             from .train_path import DarknetTrainFn, TrainPlan
@@ -439,12 +462,17 @@ class Darknet(nn.Module):
                 _lib.check(st, "ryolo_conv_bn_act_fwd")
         if not self.yolo_layers:      # trunk graph without YOLO layers: the raw head maps [B, filters, ny, nx]
             return [head for _, head in plan["heads"]]
+        return self._decode_heads([head for _, head in plan["heads"]], b, h, w, x.device)
+
+    def _decode_heads(self, heads, b, h, w, device):
+        """fp32 NCHW head maps -> (io [B, sum(na*ny*nx), nc+6], (p0, p1, p2)) like models.py:294-298"""
         nc = self.module_list[self.yolo_layers[0]].nc
-        total = sum(plan["rows"])
-        io = torch.empty((b, total, nc + 6), dtype=torch.float32, device=x.device)
+        rows = [self.module_list[yi].na * hd.shape[2] * hd.shape[3] for yi, hd in zip(self.yolo_layers, heads)]
+        total = sum(rows)
+        io = torch.empty((b, total, nc + 6), dtype=torch.float32, device=device)
         ps = []
         off = 0
-        for (ci, head), yi, r in zip(plan["heads"], self.yolo_layers, plan["rows"]):
+        for head, yi, r in zip(heads, self.yolo_layers, rows):
             ps.append(self.module_list[yi].decode_into(head, (h, w), io, total, off))
             off += r
         return io, tuple(ps)

@@ -140,3 +140,24 @@ def non_max_suppression(prediction, conf_thres=0.5, nms_thres=0.5):
             det_max = torch.cat(det_max)
             output[image_i] = det_max[(-det_max[:, 5]).argsort()]
     return output
+
+
+def detect_postprocess(io, conf_thres, nms_thres, cap, filter_done_event=None):
+    """detect.py:204-213 after the forward: candidate filter + rotated NMS for a whole batch WITHOUT host round trips.
+    io [B, P, 6+nc] float32 CUDA (decoded predictions, modified in place like non_max_suppression does).  Per image the
+    `cap` most confident candidates enter NMS (random-init weights put ~half of the 545 832 proposals above any
+    threshold; the reference has no cap and relies on trained weights).  Returns dict(dets [B, cap, 6], keep [B, cap]
+    int64, num_keep [B] int32): image b keeps rows dets[b, keep[b, :num_keep[b]]]."""
+    bsz = io.shape[0]
+    dets, keeps, nums = [], [], []
+    for i in range(bsz):
+        cand, _num = nms_filter_async(io[i], conf_thres, 2.0, 300000)
+        top = torch.topk(cand[:, 5], cap).indices
+        dets.append(cand[top][:, :6].contiguous())
+    if filter_done_event is not None:
+        filter_done_event.record()
+    for i in range(bsz):
+        k, nk, _ws = r_nms_async(dets[i], nms_thres)
+        keeps.append(k)
+        nums.append(nk)
+    return {"dets": torch.stack(dets), "keep": torch.stack(keeps), "num_keep": torch.cat(nums)}

@@ -47,3 +47,83 @@ def allreduce_gradients(params):
     flat.div_(dist.get_world_size())
     for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
         g.copy_(f)
+
+
+class GradBuckets:
+    """Bucketed, overlapped gradient all-reduce over one flat fp32 arena (reference: train.py:169-175 wraps the model in
+    DistributedDataParallel, whose reducer does the same thing for the reference's modules).
+
+    The training plan lays its parameter gradients out in ONE flat tensor in the order backward produces them
+    (last block first); ``boundaries`` are the arena offsets where a block's gradients end.  Buckets are contiguous
+    arena ranges of at least ``bucket_bytes`` cut at block boundaries.  ``ready(offset)`` is called by backward when every
+    gradient below ``offset`` has been produced: each bucket that became complete is all-reduced asynchronously on a side
+    stream (NCCL) -- overlapping the rest of backward -- and ``finish()`` makes the caller's stream wait for all of them.
+    Device-agnostic (gloo on CPU in the tests: streams are skipped there)."""
+
+    def __init__(self, arena, boundaries, bucket_bytes=32 << 20, group=None):
+        self.arena, self.group = arena, group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        cap = max(1, bucket_bytes // arena.element_size())
+        self.buckets = []                      # (lo, hi) element ranges
+        lo = 0
+        for b in boundaries:
+            if b - lo >= cap:
+                self.buckets.append((lo, b))
+                lo = b
+        if lo < arena.numel():
+            self.buckets.append((lo, arena.numel()))
+        self.cuda = arena.is_cuda
+        self.stream = torch.cuda.Stream(device=arena.device) if self.cuda else None
+        self.reset()
+
+    def reset(self):
+        self.next = 0
+        self.works = []
+
+    def ready(self, offset):
+        """every gradient in arena[:offset] is final (as far as the caller's stream is concerned)"""
+        if self.world == 1:
+            return
+        while self.next < len(self.buckets) and self.buckets[self.next][1] <= offset:
+            lo, hi = self.buckets[self.next]
+            self.next += 1
+            view = self.arena[lo:hi]
+            if self.cuda:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.arena.device))
+                self.stream.wait_event(ev)
+                with torch.cuda.stream(self.stream):
+                    self.works.append(dist.all_reduce(view, group=self.group, async_op=True))
+            else:
+                self.works.append(dist.all_reduce(view, group=self.group, async_op=True))
+
+    def finish(self):
+        """flush the remaining buckets and make the current stream wait for every all-reduce; returns 1 / world"""
+        self.ready(self.arena.numel())
+        if self.cuda and self.works:
+            # the collectives were enqueued from the side stream; work.wait() orders them before the CURRENT stream
+            for w in self.works:
+                w.wait()
+            torch.cuda.current_stream(self.arena.device).wait_stream(self.stream)
+        else:
+            for w in self.works:
+                w.wait()
+        self.works = []
+        self.next = 0
+        return 1.0 / self.world
+
+
+class DistributedDataParallel(torch.nn.Module):
+    """Drop-in for the ``torch.nn.parallel.DistributedDataParallel(model)`` wrap of train.py:175: ``.module`` is the
+    wrapped Darknet, forward is delegated.  Instead of autograd hooks, the Darknet's own backward (train_path.py) hands
+    finished gradient buckets to GradBuckets, so the NCCL all-reduce of bucket k overlaps the backward kernels of the
+    blocks before it; the gradients autograd receives are already averaged over the ranks."""
+
+    def __init__(self, module, bucket_mb=32, process_group=None):
+        super().__init__()
+        self.module = module
+        module._ddp = {"bucket_bytes": int(bucket_mb) << 20, "group": process_group}
+        module._tplan = None          # the plan builds its buckets at construction
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)

@@ -131,7 +131,6 @@ class TrainPlan:
                     blk.sums = torch.zeros(2 * blk.cout, dtype=torch.float32, device=device)
                     blk.mean, blk.invstd, blk.scale, blk.shift = (torch.zeros(blk.cout, dtype=torch.float32, device=device)
                                                                   for _ in range(4))
-                    blk.bsums = torch.zeros(2 * blk.cout + 1, dtype=torch.float32, device=device)
                 blk.s2d = (i > 0 and blk.stride == 2 and blk.k == 3 and blk.src.h % 2 == 0 and blk.src.w % 2 == 0
                            and blk.src.c % 8 == 0)
                 if blk.s2d:
@@ -163,7 +162,6 @@ class TrainPlan:
                 if i > 0:
                     blk.pwd = torch.empty(_lib.lib.ryolo_conv_packed_weight_bytes(ctypes.byref(blk.ddesc)), dtype=torch.uint8,
                                           device=device)
-                blk.gw = torch.empty(tuple(seq.Conv2d.weight.shape), dtype=torch.float32, device=device)
                 blocks.append(blk)
                 i += 2 if (blk.fuse_res or blk.fuse_up) else 1
                 continue
@@ -188,16 +186,71 @@ class TrainPlan:
         for blk in reversed(blocks):
             blk.gres_acc = claim(blk.gres) if blk.gres is not None else False
             blk.gsrc_acc = claim(blk.gsrc) if blk.gsrc is not None else False
+        self._build_arena()
+        self.gen = 0                 # forward generation: backward must see the activations of ITS forward
+        self.consumed = True
+        self.graphs = None           # CUDA graphs of forward / backward segments (model.use_cuda_graph)
+        self.time_comm = False       # bench.py: record events around the wait for the all-reduces (exposed time)
+        self._comm_ev = None
+
+    def _build_arena(self):
+        """All parameter gradients live in ONE flat fp32 arena, laid out in the order backward produces them (last block
+        first): per block [conv weight | BN (d beta, d gamma) + PReLU d slope] (heads: [weight | bias]).  The kernels write
+        straight into it; contiguous ranges of it are the all-reduce buckets (parallel.GradBuckets) and autograd receives
+        views of a fresh scaled copy (never of plan-owned memory: AccumulateGrad may keep what it is given)."""
+        m = self.model
+        off = 0
+        self.param_slots = {}        # (block index, "Module.param") -> (offset, numel, shape)
+        bounds = []
+        for blk in reversed(self.blocks):
+            seq = m.module_list[blk.i]
+            wshape = tuple(seq.Conv2d.weight.shape)
+            n = seq.Conv2d.weight.numel()
+            blk.gw_off = off
+            self.param_slots[(blk.i, "Conv2d.weight")] = (off, n, wshape)
+            off += L.round_up(n, 4)
+            if blk.is_head:
+                if seq.Conv2d.bias is not None:
+                    blk.gb_off = off
+                    self.param_slots[(blk.i, "Conv2d.bias")] = (off, blk.cout, (blk.cout,))
+                    off += L.round_up(blk.cout, 4)
+            else:
+                blk.bs_off = off
+                self.param_slots[(blk.i, "BatchNorm2d.bias")] = (off, blk.cout, (blk.cout,))
+                self.param_slots[(blk.i, "BatchNorm2d.weight")] = (off + blk.cout, blk.cout, (blk.cout,))
+                if blk.has_act:
+                    self.param_slots[(blk.i, "activation.weight")] = (off + 2 * blk.cout, 1, (1,))
+                off += L.round_up(2 * blk.cout + 1, 4)
+            bounds.append(off)
+            blk.arena_end = off
+        self.garena = torch.zeros(off, dtype=torch.float32, device=self.device)
+        for blk in self.blocks:
+            seq = m.module_list[blk.i]
+            n = seq.Conv2d.weight.numel()
+            blk.gw = self.garena[blk.gw_off:blk.gw_off + n].view(tuple(seq.Conv2d.weight.shape))
+            if not blk.is_head:
+                blk.bsums = self.garena[blk.bs_off:blk.bs_off + 2 * blk.cout + 1]
+        ddp = getattr(m, "_ddp", None)
+        from .parallel import GradBuckets
+        self.buckets = GradBuckets(self.garena, bounds, bucket_bytes=ddp["bucket_bytes"] if ddp else (1 << 62),
+                                   group=ddp["group"] if ddp else None) if ddp else None
+        # backward segments = runs of blocks whose gradients complete one bucket (one segment without DDP)
+        segs, cur = [], []
+        ends = set(hi for _, hi in self.buckets.buckets) if self.buckets else set()
+        for blk in reversed(self.blocks):
+            cur.append(blk)
+            if blk.arena_end in ends:
+                segs.append(cur)
+                cur = []
+        if cur:
+            segs.append(cur)
+        self.segments = segs
+        self.names = [nm for nm, _ in m.named_parameters()]
 
     # ------------------------------------------------------------------------------------------------------
-    def forward(self, x):
-        m = self.model
-        lib = _lib.lib
-        st = _lib.stream_ptr(self.device)
-        _lib.check(lib.ryolo_im2col_first(_lib.ptr(x), self.batch, self.h, self.w, _lib.ptr(self.col), st), "im2col")
-        n_per_pixel = float(self.batch)
-        heads = []
+    def _slopes(self):
         # PReLU slopes stay on the device (kernels read nn.PReLU.weight through slope_dev): no host synchronisation
+        m = self.model
         for b in self.blocks:
             if b.has_act:
                 wgt = m.module_list[b.i].activation.weight
@@ -207,6 +260,18 @@ class TrainPlan:
             else:
                 b.slope_dev = None
             b.slope = 1.0
+
+    def _param_key(self):
+        """storage identity of everything the captured graphs point at"""
+        return tuple(p.data_ptr() for p in self.model.parameters()) + tuple(b.data_ptr() for b in self.model.buffers())
+
+    def _forward_body(self, x):
+        m = self.model
+        lib = _lib.lib
+        st = _lib.stream_ptr(self.device)
+        _lib.check(lib.ryolo_im2col_first(_lib.ptr(x), self.batch, self.h, self.w, _lib.ptr(self.col), st), "im2col")
+        n_per_pixel = float(self.batch)
+        self._slopes()
         bn_counters = []
         for blk in self.blocks:
             seq = m.module_list[blk.i]
@@ -220,10 +285,12 @@ class TrainPlan:
                 x_ptr = blk.xs.data_ptr()
             L.pack_weights(blk.fdesc, w, None, 2 if blk.s2d else 0, out=blk.pw)
             if blk.is_head:
-                bias = L.padded_bias(blk.fdesc, seq.Conv2d.bias.detach())
+                if getattr(blk, "bias_pad", None) is None:
+                    blk.bias_pad = L.padded_bias(blk.fdesc, torch.zeros(blk.cout, device=self.device))
+                if seq.Conv2d.bias is not None:
+                    blk.bias_pad[:blk.cout].copy_(seq.Conv2d.bias.detach())
                 _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.fdesc), ctypes.c_void_p(x_ptr), _lib.ptr(blk.pw),
-                                                     _lib.ptr(bias), None, _lib.ptr(blk.out), None, 0, st), "conv head")
-                heads.append(blk)
+                                                     _lib.ptr(blk.bias_pad), None, _lib.ptr(blk.out), None, 0, st), "conv head")
                 continue
             _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.fdesc), ctypes.c_void_p(x_ptr), _lib.ptr(blk.pw),
                                                  _lib.ptr(self.zero_bias), None, _lib.ptr(blk.z), None, 0, st), "conv")
@@ -248,83 +315,168 @@ class TrainPlan:
             with torch.no_grad():
                 torch._foreach_add_(bn_counters, 1)
         outs = []
-        for blk, yi in zip(heads, m.yolo_layers):
+        for blk, yi in zip(self.heads, m.yolo_layers):
+            layer = m.module_list[yi]
+            outs.append(blk.out.view(self.batch, layer.na, layer.nc + 6, blk.oh, blk.ow).permute(0, 1, 3, 4, 2).contiguous())
+        return outs
+
+    def forward(self, x):
+        m = self.model
+        self.heads = [b for b in self.blocks if b.is_head]
+        for blk, yi in zip(self.heads, m.yolo_layers):
             layer = m.module_list[yi]
             if (layer.nx, layer.ny) != (blk.ow, blk.oh):
                 layer.create_grids((self.h, self.w), (blk.ow, blk.oh), self.device, torch.float32)
-            outs.append(blk.out.view(self.batch, layer.na, layer.nc + 6, blk.oh, blk.ow).permute(0, 1, 3, 4, 2).contiguous())
-        self.heads = heads
+        if getattr(m, "use_cuda_graph", False):
+            outs = self._forward_graph(x)
+        else:
+            outs = self._forward_body(x)
+        self.gen += 1
+        self.consumed = False
+        return outs
+
+    # ---- CUDA-graph form (opt-in, model.use_cuda_graph): the ~1100 launches of a forward and the ~1300 of a backward are
+    # replayed as a handful of graphs -- what makes the step launch-bound at small per-GPU batches (8 GPUs: 8 images per
+    # rank) is the host, not the GPU.  Inputs are copied into static buffers; outputs are static buffers that the next
+    # step overwrites (standard CUDA-graph semantics).
+    def _forward_graph(self, x):
+        key = self._param_key()
+        if self.graphs is None or self.graphs["key"] != key:
+            self.graphs = {"key": key, "pool": None}
+            self.x_static = x.clone()
+            eager = self._forward_body(self.x_static)         # this call's forward, eagerly (also the capture warm-up)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = self._forward_body(self.x_static)      # captured, not executed
+            self.graphs["pool"] = g.pool()
+            self.graphs["fwd"] = (g, outs)
+            return eager
+        g, outs = self.graphs["fwd"]
+        self.x_static.copy_(x)
+        g.replay()
         return outs
 
     # ------------------------------------------------------------------------------------------------------
-    def backward(self, grads):
+    def _head_grads(self, grads):
+        """autograd's head cotangents [B, na, ny, nx, no] -> bias gradients + padded-NHWC bf16 dz of the head convs"""
+        lib = _lib.lib
+        st = _lib.stream_ptr(self.device)
+        for blk, g in zip(self.heads, grads):
+            g = g.contiguous().float()
+            na, no = g.shape[1], g.shape[4]
+            if (blk.i, "Conv2d.bias") in self.param_slots:
+                torch.sum(g, (0, 2, 3), out=self.garena[blk.gb_off:blk.gb_off + blk.cout].view(na, no))
+            _lib.check(lib.ryolo_head_grad_to_padded(_lib.ptr(g), self.batch, na, no, blk.oh, blk.ow, _lib.ptr(blk.dz),
+                                                     blk.zcs, st), "head_grad_to_padded")
+
+    def _backward_block(self, blk):
         m = self.model
         lib = _lib.lib
         st = _lib.stream_ptr(self.device)
-        pgrads = {}
-        for blk, g, yi in zip(self.heads, grads, m.yolo_layers):
-            layer = m.module_list[yi]
-            # g: [B, na, ny, nx, no] fp32 as autograd delivers it; filter index of the head conv = a * no + k
-            g = g.contiguous().float()
-            na, no = g.shape[1], g.shape[4]
-            pgrads[(blk.i, "Conv2d.bias")] = g.sum((0, 2, 3)).reshape(-1)
-            _lib.check(lib.ryolo_head_grad_to_padded(_lib.ptr(g), self.batch, na, no, blk.oh, blk.ow, _lib.ptr(blk.dz),
-                                                     blk.zcs, st), "head_grad_to_padded")
-        for blk in reversed(self.blocks):
-            seq = m.module_list[blk.i]
-            if blk.is_head:
-                dz = blk.dz
-            else:
-                _lib.check(lib.ryolo_bn_act_bwd(ctypes.c_void_p(blk.gy.ptr), blk.gy.cs, int(blk.fuse_up), _lib.ptr(blk.z),
-                                                blk.zcs, self.batch, blk.oh, blk.ow, blk.cout, _lib.ptr(blk.scale),
-                                                _lib.ptr(blk.shift), _lib.ptr(blk.mean), _lib.ptr(blk.invstd), blk.slope,
-                                                int(blk.has_act), 1, _lib.ptr(blk.bsums),
-                                                ctypes.c_void_p(blk.gres.ptr) if blk.gres is not None else None,
-                                                blk.gres.cs if blk.gres is not None else 0, int(blk.gres_acc),
-                                                ctypes.c_void_p(blk.slope_dev), st),
-                           "bn_act_bwd")
-                pgrads[(blk.i, "BatchNorm2d.bias")] = blk.bsums[:blk.cout]
-                pgrads[(blk.i, "BatchNorm2d.weight")] = blk.bsums[blk.cout:2 * blk.cout]
-                if blk.has_act:
-                    pgrads[(blk.i, "activation.weight")] = blk.bsums[2 * blk.cout:]
-                dz = blk.z
-            blk.dw.zero_()
-            w = seq.Conv2d.weight.detach()
-            if blk.s2d:
-                _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.zcs, blk.cout_pad, _lib.ptr(blk.xs), blk.xs_cs,
-                                                blk.cin_pad, self.batch, blk.src.h // 2, blk.src.w // 2, 2, _lib.ptr(blk.dw),
-                                                st), "wgrad s2d")
-                _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 2, blk.cout, blk.src.c, 3,
-                                                       _lib.ptr(blk.gw), st), "unpack wgrad s2d")
-                pgrads[(blk.i, "Conv2d.weight")] = blk.gw
-                L.pack_weights(blk.ddesc, w, None, 3, out=blk.pwd)          # mirrored 2x2 taps, transposed, in the pack kernel
-                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(blk.pwd),
-                                                     _lib.ptr(self.zero_bias), None, _lib.ptr(blk.dxs), None, 0, st), "dgrad s2d")
-                _lib.check(lib.ryolo_depth_to_space(_lib.ptr(blk.dxs), blk.xs_cs, self.batch, blk.src.h, blk.src.w, blk.src.c,
-                                                    ctypes.c_void_p(blk.gsrc.ptr), blk.gsrc.cs, int(blk.gsrc_acc), st), "d2s")
-                continue
-            if blk.stride == 2:
-                _lib.check(lib.ryolo_zero_insert2x(_lib.ptr(dz), blk.zcs, self.batch, blk.oh, blk.ow, blk.zcs,
-                                                   _lib.ptr(blk.dz_up), blk.zcs, blk.src.h, blk.src.w, st), "zero_insert")
-                dz = blk.dz_up
-            _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.zcs, blk.cout_pad, ctypes.c_void_p(blk.src.ptr), blk.src.cs,
-                                            blk.cin_pad, self.batch, blk.src.h, blk.src.w, blk.k_eff, _lib.ptr(blk.dw), st),
-                       "wgrad")
-            _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 0, blk.cout, blk.cin, blk.k_eff,
-                                                   _lib.ptr(blk.gw), st), "unpack wgrad")
-            pgrads[(blk.i, "Conv2d.weight")] = blk.gw
-            if blk.i > 0:
-                gp = blk.gsrc.ptr
-                blk.ddesc.has_residual = int(blk.gsrc_acc)
-                L.pack_weights(blk.ddesc, w, None, 1, out=blk.pwd)          # taps mirrored + transposed in the pack kernel
-                _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(blk.pwd),
-                                                     _lib.ptr(self.zero_bias), ctypes.c_void_p(gp) if blk.gsrc_acc else None,
-                                                     ctypes.c_void_p(gp), None, 0, st), "dgrad")
+        seq = m.module_list[blk.i]
+        if blk.is_head:
+            dz = blk.dz
+        else:
+            _lib.check(lib.ryolo_bn_act_bwd(ctypes.c_void_p(blk.gy.ptr), blk.gy.cs, int(blk.fuse_up), _lib.ptr(blk.z),
+                                            blk.zcs, self.batch, blk.oh, blk.ow, blk.cout, _lib.ptr(blk.scale),
+                                            _lib.ptr(blk.shift), _lib.ptr(blk.mean), _lib.ptr(blk.invstd), blk.slope,
+                                            int(blk.has_act), 1, _lib.ptr(blk.bsums),
+                                            ctypes.c_void_p(blk.gres.ptr) if blk.gres is not None else None,
+                                            blk.gres.cs if blk.gres is not None else 0, int(blk.gres_acc),
+                                            ctypes.c_void_p(blk.slope_dev), st),
+                       "bn_act_bwd")
+            dz = blk.z
+        blk.dw.zero_()
+        w = seq.Conv2d.weight.detach()
+        if blk.s2d:
+            _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.zcs, blk.cout_pad, _lib.ptr(blk.xs), blk.xs_cs,
+                                            blk.cin_pad, self.batch, blk.src.h // 2, blk.src.w // 2, 2, _lib.ptr(blk.dw),
+                                            st), "wgrad s2d")
+            _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 2, blk.cout, blk.src.c, 3,
+                                                   _lib.ptr(blk.gw), st), "unpack wgrad s2d")
+            L.pack_weights(blk.ddesc, w, None, 3, out=blk.pwd)          # mirrored 2x2 taps, transposed, in the pack kernel
+            _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(blk.pwd),
+                                                 _lib.ptr(self.zero_bias), None, _lib.ptr(blk.dxs), None, 0, st), "dgrad s2d")
+            _lib.check(lib.ryolo_depth_to_space(_lib.ptr(blk.dxs), blk.xs_cs, self.batch, blk.src.h, blk.src.w, blk.src.c,
+                                                ctypes.c_void_p(blk.gsrc.ptr), blk.gsrc.cs, int(blk.gsrc_acc), st), "d2s")
+            return
+        if blk.stride == 2:
+            _lib.check(lib.ryolo_zero_insert2x(_lib.ptr(dz), blk.zcs, self.batch, blk.oh, blk.ow, blk.zcs,
+                                               _lib.ptr(blk.dz_up), blk.zcs, blk.src.h, blk.src.w, st), "zero_insert")
+            dz = blk.dz_up
+        _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.zcs, blk.cout_pad, ctypes.c_void_p(blk.src.ptr), blk.src.cs,
+                                        blk.cin_pad, self.batch, blk.src.h, blk.src.w, blk.k_eff, _lib.ptr(blk.dw), st),
+                   "wgrad")
+        _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 0, blk.cout, blk.cin, blk.k_eff,
+                                               _lib.ptr(blk.gw), st), "unpack wgrad")
+        if blk.i > 0:
+            gp = blk.gsrc.ptr
+            blk.ddesc.has_residual = int(blk.gsrc_acc)
+            L.pack_weights(blk.ddesc, w, None, 1, out=blk.pwd)          # taps mirrored + transposed in the pack kernel
+            _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(blk.pwd),
+                                                 _lib.ptr(self.zero_bias), ctypes.c_void_p(gp) if blk.gsrc_acc else None,
+                                                 ctypes.c_void_p(gp), None, 0, st), "dgrad")
+
+    def backward(self, grads):
+        m = self.model
+        self._head_grads(grads)
+        use_graph = getattr(m, "use_cuda_graph", False) and self.graphs is not None and "fwd" in self.graphs
+        if use_graph and "bwd" not in self.graphs:
+            # first backward after capture of the forward: run eagerly once (warm-up), then capture every segment
+            for seg in self.segments:
+                for blk in seg:
+                    self._backward_block(blk)
+                if self.buckets:
+                    self.buckets.ready(seg[-1].arena_end)
+            inv = self.buckets.finish() if self.buckets else 1.0
+            out_flat = self.garena * inv
+            torch.cuda.synchronize(self.device)
+            gs = []
+            for seg in self.segments:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self.graphs["pool"]):
+                    for blk in seg:
+                        self._backward_block(blk)
+                gs.append(g)
+            self.graphs["bwd"] = gs
+            # the capture passes did not execute; the eager pass above produced this step's gradients
+        else:
+            for si, seg in enumerate(self.segments):
+                if use_graph:
+                    self.graphs["bwd"][si].replay()
+                else:
+                    for blk in seg:
+                        self._backward_block(blk)
+                if self.buckets:
+                    self.buckets.ready(seg[-1].arena_end)     # NCCL all-reduce of the finished bucket on the side stream
+            if self.time_comm:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            inv = self.buckets.finish() if self.buckets else 1.0
+            if self.time_comm:
+                e1.record()
+                self._comm_ev = (e0, e1)
+            out_flat = self.garena * inv                       # fresh tensor: autograd may keep what it is given
+        self.consumed = True
         out = []
-        for name, p in m.named_parameters():
+        for name in self.names:
             parts = name.split(".")            # module_list.{i}.{Module}.{param}
-            out.append(pgrads.get((int(parts[1]), parts[2] + "." + parts[3])))
+            slot = self.param_slots.get((int(parts[1]), parts[2] + "." + parts[3]))
+            out.append(out_flat[slot[0]:slot[0] + slot[1]].view(slot[2]) if slot is not None else None)
         return out
+
+
+def _comm_wait_ms(self):
+    """time the main stream spent waiting for the gradient all-reduces AFTER the last backward kernel was enqueued = the
+    exposed (non-overlapped) part of the collective; None when not measured"""
+    if self._comm_ev is None:
+        return None
+    self._comm_ev[1].synchronize()
+    return self._comm_ev[0].elapsed_time(self._comm_ev[1])
+
+
+TrainPlan.last_comm_wait_ms = _comm_wait_ms
 
 
 def _mk_view(buf, ch_off, c, h, w):
@@ -337,9 +489,23 @@ class DarknetTrainFn(torch.autograd.Function):
     def forward(ctx, plan, x, *params):
         ctx.plan = plan
         outs = plan.forward(x)
+        ctx.gen = plan.gen
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *grads):
-        pg = ctx.plan.backward([g.contiguous() for g in grads])
+        plan = ctx.plan
+        if plan.gen != ctx.gen or plan.consumed:
+            # activations live in the plan (not per call): a second forward overwrote them, or a backward already turned
+            # z into dz in place.  Stock autograd would handle or reject these cases; silently wrong gradients are not an option.
+            raise RuntimeError("Darknet training plan: the activations of this forward were overwritten by a later forward "
+                               "or already consumed by a backward (retain_graph / two forwards before one backward are "
+                               "not supported by the fused training path)")
+        gl = []
+        for g, blk, yi in zip(grads, plan.heads, plan.model.yolo_layers):
+            if g is None:
+                layer = plan.model.module_list[yi]
+                g = torch.zeros((plan.batch, layer.na, blk.oh, blk.ow, layer.nc + 6), dtype=torch.float32, device=plan.device)
+            gl.append(g)
+        pg = plan.backward(gl)
         return (None, None) + tuple(pg)

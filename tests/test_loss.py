@@ -44,7 +44,7 @@ def test_compute_loss_vs_reference():
 
 def test_orphan_ground_truth_gets_an_anchor():
     """a GT matching no anchor by IoU/angle is assigned its best anchor (loss.py:235-242)"""
-    from rotate_yolov3_b200.loss import build_targets
+    from loss_indexed import build_targets
     g = np.load(os.path.join(GOLDEN, "loss_golden.npz"))
     hyp = {str(k): float(v) for k, v in zip(g["hyp_keys"], g["hyp_vals"])}
     ps = [torch.from_numpy(g["p%d" % k]) for k in range(3)]
@@ -60,7 +60,11 @@ def test_orphan_ground_truth_gets_an_anchor():
 def test_masked_loss_equals_indexed_loss():
     """the synchronisation-free formulation (all (anchor, target) rows + assignment mask) reproduces the literal indexed
     formulation: value, components and gradients; random targets including orphans, duplicated cells, and nc > 1"""
-    from rotate_yolov3_b200.loss import compute_loss
+    from loss_indexed import compute_loss_indexed
+    from rotate_yolov3_b200.loss import compute_loss as compute_loss_masked
+
+    def compute_loss(ps, t, m, hyp, masked):
+        return compute_loss_masked(ps, t, m, hyp) if masked else compute_loss_indexed(ps, t, m, hyp)
     g = np.load(os.path.join(GOLDEN, "loss_golden.npz"))
     hyp = {str(k): float(v) for k, v in zip(g["hyp_keys"], g["hyp_vals"])}
     gen = torch.Generator().manual_seed(3)
@@ -81,9 +85,15 @@ def test_masked_loss_equals_indexed_loss():
             m.nc = nc
             if nc > 1:
                 # the reference's multi-class branch feeds BCE a [nb, nc+1] input and a [nb, nc] target
-                # (model/loss.py:331-333) and raises; both formulations keep that behaviour
-                with pytest.raises(ValueError):
-                    compute_loss(ps, t.clone(), m, hyp, masked=masked)
+                # (model/loss.py:331-333) and raises -- the literal restatement keeps that; the product evaluates the
+                # evidently intended class columns ps[:, 6:] instead of crashing
+                if masked:
+                    loss, items = compute_loss(ps, t.clone(), m, hyp, masked=True)
+                    loss.backward()
+                    assert torch.isfinite(loss).all() and float(items[1]) > 0
+                else:
+                    with pytest.raises(ValueError):
+                        compute_loss(ps, t.clone(), m, hyp, masked=False)
                 continue
             loss, items = compute_loss(ps, t.clone(), m, hyp, masked=masked)
             loss.backward()
@@ -100,7 +110,8 @@ def test_masked_loss_equals_indexed_loss():
 def test_masked_assignment_selects_the_rows_build_targets_keeps():
     """_targets_masked (fixed shapes + mask, vectorised orphan rescue) marks exactly the (layer, anchor, target) rows that
     build_targets returns after its data-dependent filtering -- same indices, boxes and anchors, in the same order"""
-    from rotate_yolov3_b200.loss import _targets_masked, build_targets
+    from loss_indexed import build_targets
+    from rotate_yolov3_b200.loss import _targets_masked
     g = np.load(os.path.join(GOLDEN, "loss_golden.npz"))
     hyp = {str(k): float(v) for k, v in zip(g["hyp_keys"], g["hyp_vals"])}
     ps = [torch.from_numpy(g["p%d" % k]) for k in range(3)]
@@ -125,3 +136,33 @@ def test_masked_assignment_selects_the_rows_build_targets_keeps():
             assert torch.equal(r["av"][k], av[lid])
             for name, ref in zip(("b", "a", "gj", "gi"), indices[lid]):
                 assert torch.equal(r[name][k], ref)
+
+
+def test_loss_without_targets_and_with_poisoned_unselected_rows():
+    """no ground truth -> objectness only (the reference's `if nb:` skip); rows the assignment mask rejects must not leak
+    inf/NaN into value or gradient (exp() of a huge raw value times a 0 mask is NaN)"""
+    from rotate_yolov3_b200.loss import compute_loss
+    g = np.load(os.path.join(GOLDEN, "loss_golden.npz"))
+    hyp = {str(k): float(v) for k, v in zip(g["hyp_keys"], g["hyp_vals"])}
+    ps = [torch.from_numpy(g["p%d" % k]).clone().requires_grad_(True) for k in range(3)]
+    m = _fake_model(ps, hyp)
+    loss, items = compute_loss(ps, torch.zeros(0, 7), m, hyp)
+    assert float(items[1]) == 0 and float(items[2]) == 0 and torch.isfinite(loss).all()
+    loss.backward()
+    # poison exactly the (anchor, cell) positions of rows the assignment REJECTS (and that no accepted row shares)
+    from rotate_yolov3_b200.loss import _targets_masked
+    tg = torch.from_numpy(g["targets"]).clone()
+    rows = _targets_masked(m, tg.clone(), hyp)
+    ps2 = []
+    n_poisoned = 0
+    for p, r in zip(ps, rows):
+        q = p.detach().clone()
+        key = ((r["b"] * q.shape[1] + r["a"]) * q.shape[2] + r["gj"]) * q.shape[3] + r["gi"]
+        bad = ~torch.isin(key, key[r["mask"]]) & ~r["mask"]
+        q.view(-1, q.shape[-1])[key[bad], 2:4] = 200.0          # exp(200) = inf in fp32
+        n_poisoned += int(bad.sum())
+        ps2.append(q.requires_grad_(True))
+    assert n_poisoned > 0
+    loss2, _ = compute_loss(ps2, tg.clone(), m, hyp)
+    loss2.backward()
+    assert torch.isfinite(loss2).all() and all(torch.isfinite(p.grad).all() for p in ps2)

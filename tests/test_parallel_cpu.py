@@ -41,6 +41,20 @@ def _worker(rank, world, port, n_total):
     assert torch.allclose(params[0].grad, torch.full((3, 2), mean))
     assert torch.allclose(params[1].grad, torch.arange(5, dtype=torch.float32) * mean)
     assert params[2].grad is None
+    # bucketed all-reduce over a flat arena (what Darknet's backward drives on the GPU with NCCL): buckets are cut at
+    # block boundaries, launched as soon as their last gradient is final, and the result is the SUM (finish() returns
+    # the 1/world factor the caller applies)
+    arena = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    bounds = [100, 130, 400, 410, 900, 1000]
+    gb = P.GradBuckets(arena, bounds, bucket_bytes=4 * 250)
+    assert gb.buckets == [(0, 400), (400, 900), (900, 1000)] and gb.world == world
+    gb.ready(130)
+    assert gb.next == 0
+    gb.ready(410)
+    assert gb.next == 1 and len(gb.works) == 1
+    inv = gb.finish()
+    assert inv == 1.0 / world and gb.next == 0 and not gb.works
+    assert torch.allclose(arena * inv, torch.arange(1000, dtype=torch.float32) * mean)
     dist.destroy_process_group()
 
 
