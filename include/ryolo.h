@@ -71,6 +71,29 @@ int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out, int32_t* 
 int ryolo_rnms_full_mask(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched ("segmented") form: `segments` independent NMS problems -- one per (image, class) -- in ONE set of launches
+ * (reference: the per-image / per-class Python loop of non_max_suppression, utils/nms/nms.py:28-69, calling r_nms once
+ * per class).  Segment s owns rows [s*cap, s*cap + n_dev[s]) of dets [segments*cap, 6]; its counts come from DEVICE
+ * memory (ryolo_detect_select), so nothing synchronises with the host.  At most `limit` boxes per segment -- the
+ * best-scored, ties by row index -- enter the NMS.  keep_out [segments, cap] int64: kept row indices WITHIN the segment,
+ * ascending; num_keep [segments] int32.  Same kernels and same pinned arithmetic as ryolo_rnms (which is the
+ * segments = 1, host-count case): per segment the kept list is bit-identical to r_nms on that segment's boxes. */
+size_t ryolo_rnms_batched_workspace_bytes(int segments, int cap);
+int ryolo_rnms_batched(const float* dets, int segments, int cap, const int32_t* n_dev, int limit, float thr,
+                       int64_t* keep_out, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* Batched candidate selection in front of it (reference: utils/nms/nms.py:34-40 per image; detect.py:204-213).
+ * io [batch, p, 6+nc] fp32 decoded predictions (NOT modified).  Per image: rows passing the reference's filter
+ * (conf = obj * max class conf > conf_thres, w and h > min_wh, all values finite) whose conf lies in or above the
+ * histogram bin (4096 linear bins on [0,1]) of the limit-th largest conf are written IN INPUT ORDER to
+ * dets_out [batch, cap, 6] = (x, y, w, h, theta, conf); n_out [batch] int32 = their number (<= cap; cap >= limit,
+ * the surplus over limit is at most one bin's population and is cut by ryolo_rnms_batched's `limit`). */
+size_t ryolo_detect_select_workspace_bytes(int batch, int p);
+int ryolo_detect_select(const float* io, int batch, int p, int nc, float conf_thres, float min_wh, int limit,
+                        float* dets_out, int cap, int32_t* n_out, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* Introspection of the last ryolo_rnms_full_mask call that used `workspace` (valid until the workspace is
  * reused): device pointers to the score-sorted boxes [n,6], the sort permutation order[n]
  * (int32, sorted position -> original index) and the suppression mask [n, ceil(n/64)] uint64 in the
@@ -97,6 +120,23 @@ int ryolo_riou_paired(const float* a, const float* b, int n, int stride_a, int s
 /* out[i*m + j] = iou(a_i, b_j)  (the reference's 1-vs-N form applied to every row of a) */
 int ryolo_riou_pairwise(const float* a, int n, int stride_a, const float* b, int m, int stride_b,
                         int mode, float* out, void* stream);
+
+/* Rotated IoU as a differentiable op (the README's "riou loss", which model/loss.py does not
+ * implement): iou_out[i] = IoU(a_i, b_i) (mode 'iou' semantics as above) and, given grad_out[i] = dL/d iou_i (NULL = 1),
+ * the analytic gradients grad_a / grad_b [n, 5] w.r.t. (cx, cy, w, h, theta) of each box (boundary-velocity formula:
+ * d area(a ∩ b) = integral over the part of the moving box's boundary inside the other box of its normal velocity;
+ * riou_grad.cu).  Any of iou_out / grad_a / grad_b may be NULL. */
+int ryolo_riou_paired_grad(const float* a, const float* b, int n, int stride_a, int stride_b,
+                           const float* grad_out, float* iou_out, float* grad_a, float* grad_b, void* stream);
+
+/* Greedy prediction <-> ground-truth assignment of the mAP evaluation (reference test.py:134-151) on the device.
+ * iou [p, t] (row stride iou_stride) = ryolo_riou_pairwise of the image's confidence-sorted predictions against its
+ * targets; pcls: class of prediction i at pcls[i * pcls_stride]; tcls [t].  In order, a prediction is correct when the
+ * best-IoU target OF ITS CLASS (first maximum) has IoU > iou_thres and was not claimed before; the walk stops once every
+ * target is claimed.  correct [p] uint8; claimed_scratch [t] uint8. */
+int ryolo_match_detections(const float* iou, int p, int t, int iou_stride, const float* pcls, int pcls_stride,
+                           const float* tcls, float iou_thres, unsigned char* claimed_scratch,
+                           unsigned char* correct, void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * non_max_suppression candidate filter (reference: utils/nms/nms.py:34-40, 55)

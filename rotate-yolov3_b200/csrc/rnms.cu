@@ -12,6 +12,7 @@
 //     through a shared-memory queue so the ~1k-instruction exact path runs with full warps;
 //   * the 50 MB mask never leaves HBM: the greedy scan runs on the device.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 #include <cub/util_type.cuh>
 
 #include "common.cuh"
@@ -34,28 +35,62 @@ enum {
   F_HW = 22, F_HH = 23
 };
 
-__global__ void rnms_keys_kernel(const float* __restrict__ dets, int n, float* __restrict__ keys,
-                                 int* __restrict__ vals) {
+// Segments: S independent NMS problems (one per (image, class)) in ONE set of launches.  Segment s owns rows
+// [s*cap, s*cap + count_s) of dets; count_s comes from device memory (the candidate selection never visits the host) or
+// from the host (the single-problem r_nms entry point); at most `limit` boxes (the best-scored) enter the NMS.
+struct SegArgs {
+  const int* n_dev;   // [S] candidate counts, or nullptr: every segment has n_host boxes
+  int n_host;
+  int limit;          // boxes entering NMS per segment = min(count, limit)
+  int cap;            // rows per segment of dets / keys / order / keep_out
+  int n_pad;          // cap rounded up to the tile size: stride of the geometry arrays / keep flags / mask rows
+  int cbs;            // n_pad / 64: words per mask row, entries of remv / keptw per segment
+};
+__device__ __forceinline__ int seg_count(const SegArgs& a, int seg) {
+  const int n = a.n_dev ? a.n_dev[seg] : a.n_host;
+  return n < 0 ? 0 : (n < a.cap ? n : a.cap);
+}
+__device__ __forceinline__ int seg_n(const SegArgs& a, int seg) {
+  const int n = seg_count(a, seg);
+  return n < a.limit ? n : a.limit;
+}
+
+__global__ void rnms_keys_kernel(const float* __restrict__ dets, SegArgs sa, float* __restrict__ keys,
+                                 int* __restrict__ vals, int* __restrict__ seg_begin, int* __restrict__ seg_end) {
+  const int seg = blockIdx.y;
+  const int n = seg_count(sa, seg);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && seg_begin) {
+    seg_begin[seg] = seg * sa.cap;
+    seg_end[seg] = seg * sa.cap + n;
+  }
   if (i < n) {
-    keys[i] = dets[(size_t)i * 6 + 5];
-    vals[i] = i;
+    keys[(size_t)seg * sa.cap + i] = dets[((size_t)seg * sa.cap + i) * 6 + 5];
+    vals[(size_t)seg * sa.cap + i] = i;
   }
 }
 
 // One thread per score-sorted box: gather, pinned corner arithmetic, filter data.
-__global__ void rnms_prep_kernel(const float* __restrict__ dets, const int* __restrict__ order_in, int n,
-                                 int n_pad, float* __restrict__ sorted_boxes, int* __restrict__ order_out,
+__global__ void rnms_prep_kernel(const float* __restrict__ dets, const int* __restrict__ order_in, SegArgs sa,
+                                 float* __restrict__ sorted_boxes, int* __restrict__ order_out,
                                  float* __restrict__ geom, unsigned char* __restrict__ keep_flag) {
+  const int seg = blockIdx.y;
+  const int n = seg_n(sa, seg), n_pad = sa.n_pad;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
+  dets += (size_t)seg * sa.cap * 6;
+  order_in += (size_t)seg * sa.cap;
+  sorted_boxes += (size_t)seg * sa.cap * 6;
+  order_out += (size_t)seg * sa.cap;
+  geom += (size_t)seg * kGeomFields * n_pad;
+  keep_flag += (size_t)seg * n_pad;
+  keep_flag[i] = 0;                       // flags are indexed by ORIGINAL row (< count <= cap <= n_pad)
   float g[kGeomFields];
 #pragma unroll
   for (int f = 0; f < kGeomFields; f++) g[f] = 0.f;
   if (i < n) {
     const int src = order_in[i];
     order_out[i] = src;
-    keep_flag[i] = 0;
     float b[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -138,15 +173,20 @@ __device__ __forceinline__ bool surely_disjoint(float rcx, float rcy, float rrad
 // `remv` (optional): suppression state at launch time (bit set = box already suppressed by a kept box of an earlier
 // row chunk).  Rows and columns that are already suppressed are skipped: their mask bits can never influence the
 // greedy scan (a suppressed row is never kept, so its mask row is never read; a suppressed column stays suppressed).
-__global__ void __launch_bounds__(MASK_THREADS, 3) rnms_mask_kernel(const float* __restrict__ geom, int n, int n_pad,
-                                                                 int col_blocks, float thr, int use_filter,
-                                                                 u64* __restrict__ mask, int rb_begin,
+__global__ void __launch_bounds__(MASK_THREADS, 3) rnms_mask_kernel(const float* __restrict__ geom, SegArgs sa, float thr,
+                                                                 int use_filter, u64* __restrict__ mask, int rb_begin,
                                                                  const u64* __restrict__ remv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MaskSmem& sm = *reinterpret_cast<MaskSmem*>(smem_raw);
+  const int seg = blockIdx.z;
+  const int n = seg_n(sa, seg), n_pad = sa.n_pad, cbs = sa.cbs;
+  const int col_blocks = (n + TB - 1) / TB;          // of THIS segment
   const int rb = rb_begin + blockIdx.y;
   const int cb0 = rb + blockIdx.x * CH;
-  if (cb0 >= col_blocks) return;
+  if (rb >= col_blocks || cb0 >= col_blocks) return;
+  geom += (size_t)seg * kGeomFields * n_pad;
+  mask += (size_t)seg * n_pad * cbs;
+  if (remv) remv += (size_t)seg * cbs;
   const u64 row_dead = remv ? remv[rb] : 0ull;
   if (row_dead == ~0ull) return;   // every row of this block is already suppressed: nothing it could contribute
   const int ncols = min(CH, col_blocks - cb0);
@@ -259,7 +299,7 @@ __global__ void __launch_bounds__(MASK_THREADS, 3) rnms_mask_kernel(const float*
   for (int e = tid; e < TB * ncols; e += MASK_THREADS) {
     const int rr = e / ncols, cc = e % ncols;
     const int row = rb * TB + rr;
-    if (row < n) mask[(size_t)row * col_blocks + cb0 + cc] = sm.mask[rr * CH + cc];
+    if (row < n) mask[(size_t)row * cbs + cb0 + cc] = sm.mask[rr * CH + cc];
   }
 }
 
@@ -281,7 +321,7 @@ __device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
 // Processes row blocks [b_begin, b_end) of the greedy scan; the suppression state `remv_g` and the kept bits `keptw_g`
 // live in global memory between launches (row chunks alternate with mask launches that skip what is already
 // suppressed).  The last launch (`final`) also compacts the kept ORIGINAL indices.
-__global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __restrict__ mask, int n, int col_blocks,
+__global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __restrict__ mask, SegArgs sa,
                                                                  const int* __restrict__ order,
                                                                  unsigned char* __restrict__ keep_flag,
                                                                  long long* __restrict__ keep_out,
@@ -289,8 +329,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __re
                                                                  u64* __restrict__ remv_g, u64* __restrict__ keptw_g,
                                                                  int final) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* remv = reinterpret_cast<u64*>(smem_raw);   // [col_blocks]
-  u64* keptw = remv + col_blocks;                  // [col_blocks] kept bits per block
+  const int seg = blockIdx.x;                      // one scan CTA per segment, all segments concurrently
+  const int n = seg_n(sa, seg), n_raw = seg_count(sa, seg), cbs = sa.cbs;
+  const int col_blocks = (n + TB - 1) / TB;        // of THIS segment
+  b_begin = min(b_begin, col_blocks);
+  b_end = min(b_end, col_blocks);
+  mask += (size_t)seg * sa.n_pad * cbs;
+  order += (size_t)seg * sa.cap;
+  keep_flag += (size_t)seg * sa.n_pad;
+  keep_out += (size_t)seg * sa.cap;
+  num_keep += seg;
+  remv_g += (size_t)seg * cbs;
+  keptw_g += (size_t)seg * cbs;
+  u64* remv = reinterpret_cast<u64*>(smem_raw);   // [cbs]
+  u64* keptw = remv + cbs;                         // [cbs] kept bits per block
   __shared__ int s_warp_sums[SCAN_THREADS / 32];
   __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -301,7 +353,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __re
   __syncthreads();
 
   auto ld = [&](int row, int word) -> u64 {
-    return (row < n && word < col_blocks) ? mask[(size_t)row * col_blocks + word] : 0ull;
+    return (row < n && word < col_blocks) ? mask[(size_t)row * cbs + word] : 0ull;
   };
   u64 dg0 = 0, dg1 = 0, nx0 = 0, nx1 = 0, ext = 0;
   if (warp == 0) {
@@ -342,7 +394,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __re
         if (j < col_blocks) {
           u64 acc = 0ull;
           u64 bits = kept;
-          const u64* base = mask + (size_t)b * TB * col_blocks + j;
+          const u64* base = mask + (size_t)b * TB * cbs + j;
           while (bits) {
             u64 v[8];
 #pragma unroll
@@ -351,7 +403,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __re
               if (bits) {
                 const int i = __ffsll((long long)bits) - 1;
                 bits &= bits - 1;
-                v[u] = base[(size_t)i * col_blocks];
+                v[u] = base[(size_t)i * cbs];
               }
             }
             acc |= ((v[0] | v[1]) | (v[2] | v[3])) | ((v[4] | v[5]) | (v[6] | v[7]));
@@ -376,10 +428,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __re
     if ((keptw[i >> 6] >> (i & 63)) & 1ull) keep_flag[order[i]] = 1;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  // compaction over ORIGINAL indices, ascending
-  for (int start = 0; start < n; start += SCAN_THREADS) {
+  // compaction over ORIGINAL indices (all count rows of the segment, not only the `limit` that entered NMS), ascending
+  for (int start = 0; start < n_raw; start += SCAN_THREADS) {
     const int i = start + tid;
-    const int flag = (i < n) ? (int)keep_flag[i] : 0;
+    const int flag = (i < n_raw) ? (int)keep_flag[i] : 0;
     const unsigned bal = __ballot_sync(0xffffffffu, flag);
     if (lane == 0) s_warp_sums[warp] = __popc(bal);
     __syncthreads();
@@ -395,9 +447,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) rnms_scan_kernel(const u64* __re
 }
 
 struct RnmsPlan {
-  int n, n_pad, col_blocks;
+  int segs, cap, n_pad, cbs;
   size_t cub_bytes;
-  // offsets
   float* sorted_boxes;
   int* order;
   float* keys[2];
@@ -407,41 +458,54 @@ struct RnmsPlan {
   unsigned char* keep_flag;
   u64* remv_g;
   u64* keptw_g;
+  int* seg_begin;
+  int* seg_end;
   void* cub_temp;
   size_t total;
 };
 
-static size_t cub_temp_bytes(int n) {
-  size_t bytes = 0;
+static size_t cub_temp_bytes(int items, int segs) {
+  size_t bytes = 0, bytes2 = 0;
   cub::DoubleBuffer<float> k(nullptr, nullptr);
   cub::DoubleBuffer<int> v(nullptr, nullptr);
-  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, k, v, n, 0, 32, (cudaStream_t)0);
+  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, k, v, items, 0, 32, (cudaStream_t)0);
   if (e != cudaSuccess) {
     cudaGetLastError();  // clear (no device in this process: size-only query)
     bytes = 0;
   }
+  e = cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, bytes2, k, v, items, segs, (const int*)nullptr,
+                                                         (const int*)nullptr, 0, 32, (cudaStream_t)0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    bytes2 = 0;
+  }
+  if (bytes2 > bytes) bytes = bytes2;
   // conservative floor so that a size computed on a GPU-less host still fits the real query
   const size_t floor_bytes = (size_t)1 << 20;
-  return bytes > floor_bytes ? bytes : floor_bytes + (size_t)16 * (size_t)(n > 0 ? n : 0);
+  return bytes > floor_bytes ? bytes : floor_bytes + (size_t)16 * (size_t)(items > 0 ? items : 0);
 }
 
-static void plan_rnms(int n, void* ws, RnmsPlan* p) {
-  p->n = n;
-  p->n_pad = (n + TB - 1) / TB * TB;
-  p->col_blocks = (n + TB - 1) / TB;
-  p->cub_bytes = cub_temp_bytes(n);
+static void plan_rnms(int segs, int cap, void* ws, RnmsPlan* p) {
+  p->segs = segs;
+  p->cap = cap;
+  p->n_pad = (cap + TB - 1) / TB * TB;
+  p->cbs = p->n_pad / TB;
+  const size_t items = (size_t)segs * cap;
+  p->cub_bytes = cub_temp_bytes((int)items, segs);
   Carver c(ws);
-  p->sorted_boxes = c.take<float>((size_t)n * 6);
-  p->order = c.take<int>(n);
-  p->keys[0] = c.take<float>(n);
-  p->keys[1] = c.take<float>(n);
-  p->vals[0] = c.take<int>(n);
-  p->vals[1] = c.take<int>(n);
-  p->geom = c.take<float>((size_t)kGeomFields * p->n_pad);
-  p->mask = c.take<u64>((size_t)n * p->col_blocks);
-  p->keep_flag = c.take<unsigned char>(n);
-  p->remv_g = c.take<u64>(2 * (size_t)p->col_blocks);
-  p->keptw_g = p->remv_g + p->col_blocks;
+  p->sorted_boxes = c.take<float>(items * 6);
+  p->order = c.take<int>(items);
+  p->keys[0] = c.take<float>(items);
+  p->keys[1] = c.take<float>(items);
+  p->vals[0] = c.take<int>(items);
+  p->vals[1] = c.take<int>(items);
+  p->geom = c.take<float>((size_t)segs * kGeomFields * p->n_pad);
+  p->mask = c.take<u64>((size_t)segs * p->n_pad * p->cbs);
+  p->keep_flag = c.take<unsigned char>((size_t)segs * p->n_pad);
+  p->remv_g = c.take<u64>(2 * (size_t)segs * p->cbs);
+  p->keptw_g = p->remv_g + (size_t)segs * p->cbs;
+  p->seg_begin = c.take<int>(2 * (size_t)segs);
+  p->seg_end = p->seg_begin + segs;
   p->cub_temp = c.take<unsigned char>(p->cub_bytes);
   p->total = align_up(c.off, 256);
 }
@@ -453,90 +517,129 @@ using namespace ryolo;
 extern "C" size_t ryolo_rnms_workspace_bytes(int n) {
   if (n <= 0) return 256;
   RnmsPlan p;
-  plan_rnms(n, nullptr, &p);
+  plan_rnms(1, n, nullptr, &p);
+  return p.total;
+}
+extern "C" size_t ryolo_rnms_batched_workspace_bytes(int segments, int cap) {
+  if (segments <= 0 || cap <= 0) return 256;
+  RnmsPlan p;
+  plan_rnms(segments, cap, nullptr, &p);
   return p.total;
 }
 
-static int rnms_impl(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep, void* workspace,
-                     size_t workspace_bytes, void* stream_, bool full_mask);
-
-extern "C" int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep, void* workspace,
-                          size_t workspace_bytes, void* stream_) {
-  return rnms_impl(dets, n, thr, keep_out, num_keep, workspace, workspace_bytes, stream_, false);
-}
-extern "C" int ryolo_rnms_full_mask(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep,
-                                    void* workspace, size_t workspace_bytes, void* stream_) {
-  return rnms_impl(dets, n, thr, keep_out, num_keep, workspace, workspace_bytes, stream_, true);
-}
-
-static int rnms_impl(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep, void* workspace,
-                     size_t workspace_bytes, void* stream_, bool full_mask) {
+static int rnms_impl(const float* dets, int segs, int cap, const int32_t* n_dev, int n_host, int limit, float thr,
+                     int64_t* keep_out, int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream_,
+                     bool full_mask) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  RYOLO_ARG_CHECK(n >= 0);
-  RYOLO_ARG_CHECK(num_keep != nullptr);
-  if (n == 0) {
-    RYOLO_CUDA_TRY(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), stream));
-    return RYOLO_OK;
-  }
-  RYOLO_ARG_CHECK(dets != nullptr && keep_out != nullptr && workspace != nullptr);
+  RYOLO_ARG_CHECK(dets != nullptr && keep_out != nullptr && workspace != nullptr && num_keep != nullptr);
+  RYOLO_ARG_CHECK(segs > 0 && segs <= 65535 && cap > 0 && limit > 0);
+  RYOLO_ARG_CHECK((long long)segs * cap < (1ll << 31));
   RYOLO_ARG_CHECK((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
   RnmsPlan p;
-  plan_rnms(n, workspace, &p);
+  plan_rnms(segs, cap, workspace, &p);
   if (p.total > workspace_bytes) {
     set_err("ryolo_rnms: workspace %zu B < required %zu B", workspace_bytes, p.total);
     return RYOLO_E_WORKSPACE;
   }
+  SegArgs sa;
+  sa.n_dev = n_dev;
+  sa.n_host = n_host;
+  sa.limit = limit;
+  sa.cap = cap;
+  sa.n_pad = p.n_pad;
+  sa.cbs = p.cbs;
   const int T = 256;
-  rnms_keys_kernel<<<(n + T - 1) / T, T, 0, stream>>>(dets, n, p.keys[0], p.vals[0]);
+  const bool segmented = segs > 1 || n_dev != nullptr;
+  rnms_keys_kernel<<<dim3((cap + T - 1) / T, segs), T, 0, stream>>>(dets, sa, p.keys[0], p.vals[0],
+                                                                   segmented ? p.seg_begin : nullptr, p.seg_end);
   RYOLO_LAUNCH_CHECK();
   cub::DoubleBuffer<float> dk(p.keys[0], p.keys[1]);
   cub::DoubleBuffer<int> dv(p.vals[0], p.vals[1]);
   size_t need = 0;
-  RYOLO_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, dk, dv, n, 0, 32, stream));
+  const int items = segs * cap;
+  if (!segmented) {
+    RYOLO_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, dk, dv, n_host, 0, 32, stream));
+  } else {
+    RYOLO_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, need, dk, dv, items, segs, p.seg_begin,
+                                                                      p.seg_end, 0, 32, stream));
+  }
   if (need > p.cub_bytes) {
     set_err("ryolo_rnms: sort scratch %zu B > planned %zu B", need, p.cub_bytes);
     return RYOLO_E_WORKSPACE;
   }
   size_t tmp = p.cub_bytes;
-  RYOLO_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(p.cub_temp, tmp, dk, dv, n, 0, 32, stream));
+  if (!segmented) {
+    RYOLO_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(p.cub_temp, tmp, dk, dv, n_host, 0, 32, stream));
+  } else {
+    // stable per-segment sort by score, descending; rows beyond a segment's count are never read
+    RYOLO_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortPairsDescending(p.cub_temp, tmp, dk, dv, items, segs, p.seg_begin,
+                                                                      p.seg_end, 0, 32, stream));
+  }
   count_launch(4);  // radix sort passes (library kernels, counted as a lower bound)
-  rnms_prep_kernel<<<(p.n_pad + T - 1) / T, T, 0, stream>>>(dets, dv.Current(), n, p.n_pad, p.sorted_boxes, p.order,
-                                                            p.geom, p.keep_flag);
+  rnms_prep_kernel<<<dim3((p.n_pad + T - 1) / T, segs), T, 0, stream>>>(dets, dv.Current(), sa, p.sorted_boxes, p.order,
+                                                                        p.geom, p.keep_flag);
   RYOLO_LAUNCH_CHECK();
   {
     RYOLO_SMEM_OPT_IN(rnms_mask_kernel, sizeof(MaskSmem));
-    const size_t smem = (size_t)p.col_blocks * sizeof(u64) * 2;
+    const size_t smem = (size_t)p.cbs * sizeof(u64) * 2;
     if (smem > 200 * 1024) {
-      set_err("ryolo_rnms: n=%d too large for the single-CTA scan (col_blocks=%d)", n, p.col_blocks);
+      set_err("ryolo_rnms: cap=%d too large for the single-CTA scan (col_blocks=%d)", cap, p.cbs);
       return RYOLO_E_UNSUPPORTED;
     }
     if (smem > 40 * 1024)
       RYOLO_CUDA_TRY(cudaFuncSetAttribute(rnms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RYOLO_CUDA_TRY(cudaMemsetAsync(p.remv_g, 0, 2 * (size_t)p.col_blocks * sizeof(u64), stream));
+    RYOLO_CUDA_TRY(cudaMemsetAsync(p.remv_g, 0, 2 * (size_t)segs * p.cbs * sizeof(u64), stream));
     // Row chunks of `chunk` blocks: mask(chunk rows x all later columns, skipping what earlier chunks suppressed),
-    // then scan(chunk).  flags & 1 (full) computes every upper-triangle tile in one launch like the reference.
-    const int chunk = full_mask ? p.col_blocks : kRowChunkBlocks;
-    for (int b0 = 0; b0 < p.col_blocks; b0 += chunk) {
-      const int b1 = b0 + chunk < p.col_blocks ? b0 + chunk : p.col_blocks;
-      dim3 grid((p.col_blocks - b0 + CH - 1) / CH, b1 - b0);
-      rnms_mask_kernel<<<grid, MASK_THREADS, sizeof(MaskSmem), stream>>>(p.geom, n, p.n_pad, p.col_blocks, thr,
-                                                                          thr >= 0.f ? 1 : 0, p.mask, b0,
+    // then scan(chunk) -- for ALL segments at once (grid z / one scan CTA per segment).  full_mask computes every
+    // upper-triangle tile in one launch like the reference.
+    const int chunk = full_mask ? p.cbs : kRowChunkBlocks;
+    for (int b0 = 0; b0 < p.cbs; b0 += chunk) {
+      const int b1 = b0 + chunk < p.cbs ? b0 + chunk : p.cbs;
+      dim3 grid((p.cbs - b0 + CH - 1) / CH, b1 - b0, segs);
+      rnms_mask_kernel<<<grid, MASK_THREADS, sizeof(MaskSmem), stream>>>(p.geom, sa, thr, thr >= 0.f ? 1 : 0, p.mask, b0,
                                                                           full_mask ? nullptr : p.remv_g);
       RYOLO_LAUNCH_CHECK();
-      rnms_scan_kernel<<<1, SCAN_THREADS, smem, stream>>>(p.mask, n, p.col_blocks, p.order, p.keep_flag,
-                                                          reinterpret_cast<long long*>(keep_out), num_keep, b0, b1,
-                                                          p.remv_g, p.keptw_g, b1 == p.col_blocks ? 1 : 0);
+      rnms_scan_kernel<<<segs, SCAN_THREADS, smem, stream>>>(p.mask, sa, p.order, p.keep_flag,
+                                                             reinterpret_cast<long long*>(keep_out), num_keep, b0, b1,
+                                                             p.remv_g, p.keptw_g, b1 == p.cbs ? 1 : 0);
       RYOLO_LAUNCH_CHECK();
     }
   }
   return RYOLO_OK;
 }
 
+static int rnms_single(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep, void* workspace,
+                       size_t workspace_bytes, void* stream_, bool full_mask) {
+  RYOLO_ARG_CHECK(n >= 0);
+  RYOLO_ARG_CHECK(num_keep != nullptr);
+  if (n == 0) {
+    RYOLO_CUDA_TRY(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream_)));
+    return RYOLO_OK;
+  }
+  return rnms_impl(dets, 1, n, nullptr, n, n, thr, keep_out, num_keep, workspace, workspace_bytes, stream_, full_mask);
+}
+
+extern "C" int ryolo_rnms(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
+  return rnms_single(dets, n, thr, keep_out, num_keep, workspace, workspace_bytes, stream_, false);
+}
+extern "C" int ryolo_rnms_full_mask(const float* dets, int n, float thr, int64_t* keep_out, int32_t* num_keep,
+                                    void* workspace, size_t workspace_bytes, void* stream_) {
+  return rnms_single(dets, n, thr, keep_out, num_keep, workspace, workspace_bytes, stream_, true);
+}
+
+extern "C" int ryolo_rnms_batched(const float* dets, int segments, int cap, const int32_t* n_dev, int limit, float thr,
+                                  int64_t* keep_out, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                                  void* stream_) {
+  RYOLO_ARG_CHECK(n_dev != nullptr);
+  return rnms_impl(dets, segments, cap, n_dev, 0, limit, thr, keep_out, num_keep, workspace, workspace_bytes, stream_, false);
+}
+
 extern "C" int ryolo_rnms_debug_views(void* workspace, int n, const float** sorted_boxes, const int32_t** order,
                                       const unsigned long long** mask) {
   RYOLO_ARG_CHECK(workspace != nullptr && n > 0);
   RnmsPlan p;
-  plan_rnms(n, workspace, &p);
+  plan_rnms(1, n, workspace, &p);
   if (sorted_boxes) *sorted_boxes = p.sorted_boxes;
   if (order) *order = p.order;
   if (mask) *mask = p.mask;

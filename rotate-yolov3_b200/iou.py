@@ -62,3 +62,52 @@ def rotated_iou_matrix(a, b, GIoU=False, out=None):
                                           _lib.stream_ptr(a.device))
     _lib.check(st, "ryolo_riou_pairwise")
     return out
+
+
+class _RotatedIoU(torch.autograd.Function):
+    """IoU of paired rotated boxes with analytic gradients w.r.t. both boxes (csrc/riou_grad.cu)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a = a[:, :5].contiguous().float()
+        b = b[:, :5].contiguous().float()
+        n = a.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            st = _lib.lib.ryolo_riou_paired_grad(_lib.ptr(a), _lib.ptr(b), n, 5, 5, None, _lib.ptr(out), None, None,
+                                                 _lib.stream_ptr(a.device))
+        _lib.check(st, "ryolo_riou_paired_grad")
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        n = a.shape[0]
+        g = g.contiguous().float()
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(a.device):
+            st = _lib.lib.ryolo_riou_paired_grad(_lib.ptr(a), _lib.ptr(b), n, 5, 5, _lib.ptr(g), None,
+                                                 _lib.ptr(ga) if ga is not None else None,
+                                                 _lib.ptr(gb) if gb is not None else None, _lib.stream_ptr(a.device))
+        _lib.check(st, "ryolo_riou_paired_grad")
+        return ga, gb
+
+
+def rotated_iou(box1, box2):
+    """differentiable IoU of paired rotated boxes: box1, box2 [N, >=5] (cx, cy, w, h, theta) CUDA -> [N]"""
+    if not (box1.is_cuda and box2.is_cuda):
+        raise RuntimeError("rotated_iou needs CUDA tensors (sm_100a kernels, no CPU fallback)")
+    return _RotatedIoU.apply(box1, box2)
+
+
+def riou_loss(pred, target, reduction="mean"):
+    """rotated-IoU regression loss 1 - IoU(pred, target) (the README's 'riou loss'; the reference's compute_loss uses
+    SmoothL1 + a horizontal wh_iou instead).  pred, target [N, 5]; gradients flow to both."""
+    loss = 1.0 - rotated_iou(pred, target)
+    if reduction == "mean":
+        return loss.mean() if loss.numel() else loss.sum()
+    if reduction == "sum":
+        return loss.sum()
+    return loss

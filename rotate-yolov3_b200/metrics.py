@@ -2,34 +2,34 @@
 
 The reference (test.py:134-151) walks the predictions of an image in Python and calls ``skew_bbox_iou(pbox, tbox[m])``
 once per prediction -- one kernel-equivalent plus a GPU<->CPU sync per box.  Here ONE rotated-IoU matrix launch covers
-the whole image and the greedy assignment runs on the small [P, T] result."""
+the whole image and ONE small kernel does the greedy assignment (class-restricted argmax per prediction, first maximum
+like torch.max, each target claimed once); the host reads the result once per image."""
 import torch
 
+from . import _lib
 from .iou import rotated_iou_matrix
 
 
-def match_detections(pred, tbox, tcls, iou_thres=0.5):
-    """pred [P, 8] = (x, y, w, h, theta, conf, cls_conf, cls), confidence-sorted as non_max_suppression returns it;
-    tbox [T, 5] pixel (x, y, w, h, theta); tcls [T].  Returns ``correct`` (list of 0/1, len P) with the reference's
-    semantics: in order, a prediction is correct if its best-IoU target OF THE SAME CLASS has IoU > iou_thres and was
-    not claimed before; stops early once every target is claimed (test.py:137-151)."""
+def match_detections_device(pred, tbox, tcls, iou_thres=0.5):
+    """pred [P, 8] = (x, y, w, h, theta, conf, cls_conf, cls) CUDA, confidence-sorted as non_max_suppression returns it;
+    tbox [T, 5] pixel (x, y, w, h, theta); tcls [T].  Returns ``correct`` as a CUDA uint8 tensor [P] (no host sync)."""
     p, t = len(pred), len(tbox)
-    correct = [0] * p
+    dev = pred.device
+    correct = torch.zeros(p, dtype=torch.uint8, device=dev)
     if p == 0 or t == 0:
         return correct
-    iou = rotated_iou_matrix(pred[:, :5].contiguous(), tbox[:, :5].contiguous().to(pred.device)).cpu()   # one launch, one copy
-    pcls = pred[:, 7].cpu()
-    tc = tcls.cpu().float()
-    tset = set(tc.tolist())
-    detected = []
-    for i in range(p):
-        if len(detected) == t:
-            break
-        if float(pcls[i]) not in tset:
-            continue
-        m = (tc == pcls[i]).nonzero().view(-1)
-        best, bi = iou[i, m].max(0)
-        if float(best) > iou_thres and int(m[bi]) not in detected:
-            correct[i] = 1
-            detected.append(int(m[bi]))
+    with torch.cuda.device(dev):
+        pred = pred.float().contiguous()
+        tb = tbox[:, :5].float().contiguous().to(dev)
+        tc = tcls.float().contiguous().to(dev)
+        iou = rotated_iou_matrix(pred[:, :5].contiguous(), tb)
+        claimed = torch.empty(t, dtype=torch.uint8, device=dev)
+        st = _lib.lib.ryolo_match_detections(_lib.ptr(iou), p, t, t, _lib.ptr(pred[:, 7:]), pred.shape[1], _lib.ptr(tc),
+                                             float(iou_thres), _lib.ptr(claimed), _lib.ptr(correct), _lib.stream_ptr(dev))
+        _lib.check(st, "ryolo_match_detections")
     return correct
+
+
+def match_detections(pred, tbox, tcls, iou_thres=0.5):
+    """same, as the list of 0/1 the reference builds (test.py:131-151): one host read per image"""
+    return match_detections_device(pred, tbox, tcls, iou_thres).tolist()

@@ -142,22 +142,52 @@ def non_max_suppression(prediction, conf_thres=0.5, nms_thres=0.5):
     return output
 
 
+def r_nms_batched(dets, counts, threshold, limit=None):
+    """S independent rotated-NMS problems in one set of launches, no host synchronisation.
+    dets [S, cap, 6] float32 CUDA contiguous, counts [S] int32 CUDA (rows used per segment), limit: at most this many
+    best-scored boxes per segment enter the NMS.  Returns (keep [S, cap] int64, num_keep [S] int32): segment s keeps rows
+    keep[s, :num_keep[s]] (ascending row indices within the segment) -- per segment identical to r_nms(dets[s, :n])."""
+    s_, cap = dets.shape[0], dets.shape[1]
+    limit = cap if limit is None else int(limit)
+    with torch.cuda.device(dets.device):
+        ws_bytes = _lib.lib.ryolo_rnms_batched_workspace_bytes(s_, cap)
+        ws = _workspace(ws_bytes, dets.device)
+        keep = torch.empty((s_, cap), dtype=torch.long, device=dets.device)
+        num = torch.empty((s_,), dtype=torch.int32, device=dets.device)
+        st = _lib.lib.ryolo_rnms_batched(_lib.ptr(dets), s_, cap, _lib.ptr(counts), limit, float(threshold), _lib.ptr(keep),
+                                         _lib.ptr(num), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dets.device))
+        _lib.check(st, "ryolo_rnms_batched")
+    return keep, num
+
+
+def detect_select(io, conf_thres, limit, min_wh=2.0, slack=2048):
+    """Candidate selection of a whole decoded batch on the device: per image the `limit` most confident rows that pass
+    the reference's filter (utils/nms/nms.py:34-40).  Returns (dets [B, limit+slack, 6], counts [B] int32)."""
+    bsz, p, no = io.shape
+    cap = int(limit) + int(slack)
+    with torch.cuda.device(io.device):
+        dets = torch.empty((bsz, cap, 6), dtype=torch.float32, device=io.device)
+        counts = torch.empty((bsz,), dtype=torch.int32, device=io.device)
+        ws_bytes = _lib.lib.ryolo_detect_select_workspace_bytes(bsz, p)
+        ws = _workspace(ws_bytes, io.device)
+        st = _lib.lib.ryolo_detect_select(_lib.ptr(io), bsz, p, no - 6, float(conf_thres), float(min_wh), int(limit),
+                                          _lib.ptr(dets), cap, _lib.ptr(counts), _lib.ptr(ws), ws_bytes,
+                                          _lib.stream_ptr(io.device))
+        _lib.check(st, "ryolo_detect_select")
+    return dets, counts
+
+
 def detect_postprocess(io, conf_thres, nms_thres, cap, filter_done_event=None):
-    """detect.py:204-213 after the forward: candidate filter + rotated NMS for a whole batch WITHOUT host round trips.
-    io [B, P, 6+nc] float32 CUDA (decoded predictions, modified in place like non_max_suppression does).  Per image the
-    `cap` most confident candidates enter NMS (random-init weights put ~half of the 545 832 proposals above any
-    threshold; the reference has no cap and relies on trained weights).  Returns dict(dets [B, cap, 6], keep [B, cap]
-    int64, num_keep [B] int32): image b keeps rows dets[b, keep[b, :num_keep[b]]]."""
-    bsz = io.shape[0]
-    dets, keeps, nums = [], [], []
-    for i in range(bsz):
-        cand, _num = nms_filter_async(io[i], conf_thres, 2.0, 300000)
-        top = torch.topk(cand[:, 5], cap).indices
-        dets.append(cand[top][:, :6].contiguous())
+    """detect.py:204-213 after the forward, for a whole batch WITHOUT host round trips: device-side candidate selection
+    (filter + top-`cap` by confidence; the reference has no cap and relies on trained weights, a random-init network puts
+    ~half of the 545 832 proposals above any threshold) and ONE segmented rotated NMS over all images (single-class
+    configs: one segment per image).  io [B, P, 6+nc] float32 CUDA contiguous.
+    Returns dict(dets [B, cap+slack, 6], counts [B], keep [B, cap+slack] int64, num_keep [B] int32): image b keeps rows
+    dets[b, keep[b, :num_keep[b]]]."""
+    if not io.is_contiguous():
+        io = io.contiguous()
+    dets, counts = detect_select(io, conf_thres, cap)
     if filter_done_event is not None:
         filter_done_event.record()
-    for i in range(bsz):
-        k, nk, _ws = r_nms_async(dets[i], nms_thres)
-        keeps.append(k)
-        nums.append(nk)
-    return {"dets": torch.stack(dets), "keep": torch.stack(keeps), "num_keep": torch.cat(nums)}
+    keep, num = r_nms_batched(dets, counts, nms_thres, limit=cap)
+    return {"dets": dets, "counts": counts, "keep": keep, "num_keep": num}

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 import torch
 
+import helpers
 from helpers import GOLDEN, I64P, P, adversarial_dets, gen_dets, orc_rnms, ref_lib
 
 pytestmark = pytest.mark.gpu
@@ -172,3 +173,84 @@ def test_full_size_config3_properties():
     if ref_lib("cuda") is not None:
         assert np.array_equal(k, _ref_cuda_keep(dets.numpy(), thr))
     assert 7000 < len(k) < 10000  # K = 8666 for this distribution
+
+
+def test_batched_segments_equal_single_problem_nms():
+    """ryolo_rnms_batched: S independent problems with device-side counts in one set of launches -> per segment the kept
+    list equals r_nms on that segment's rows (which is bit-identical to the reference kernel, tests above); includes empty,
+    single-box, ragged and full segments, and `limit` < count (only the best-scored boxes enter the NMS)."""
+    import rotate_yolov3_b200 as pkg
+    from rotate_yolov3_b200.nms import r_nms_batched
+    dev = torch.device("cuda")
+    cap = 3000
+    counts = [0, 1, 100, 1777, 3000, 2500]
+    dets = torch.zeros((len(counts), cap, 6))
+    for s, n in enumerate(counts):
+        if n:
+            dets[s, :n] = helpers.gen_dets(n, 50 + s, 300.0)
+        dets[s, n:] = float("nan")                      # rows beyond the count must never be read
+    dets = dets.to(dev)
+    cnt = torch.tensor(counts, dtype=torch.int32, device=dev)
+    for thr in (0.1, 0.5):
+        keep, num = r_nms_batched(dets, cnt, thr)
+        for s, n in enumerate(counts):
+            got = keep[s, :int(num[s])].cpu()
+            want = pkg.r_nms(dets[s, :n], thr).cpu() if n else torch.empty(0, dtype=torch.long)
+            assert torch.equal(got, want), (thr, s, n, len(got), len(want))
+    # limit: the top-`limit` boxes by score (stable) enter the NMS; kept indices still refer to the segment's rows
+    limit = 1000
+    keep, num = r_nms_batched(dets, cnt, 0.3, limit=limit)
+    for s, n in enumerate(counts):
+        got = keep[s, :int(num[s])].cpu()
+        if n == 0:
+            assert len(got) == 0
+            continue
+        sub = dets[s, :n]
+        top = torch.argsort(sub[:, 5], descending=True, stable=True)[:limit]
+        top_sorted = torch.sort(top).values
+        want = top_sorted[pkg.r_nms(sub[top_sorted], 0.3)].cpu()
+        assert torch.equal(got, want), (s, n, len(got), len(want))
+
+
+def test_detect_select_and_batched_postprocess_equal_per_image_pipeline():
+    """device-side candidate selection (histogram threshold + ordered compaction) + segmented NMS == the per-image
+    pipeline of round 1 (nms_filter -> top-k by confidence -> r_nms), image by image"""
+    import rotate_yolov3_b200 as pkg
+    from rotate_yolov3_b200.nms import detect_postprocess, detect_select, nms_filter
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    B, P, cap = 3, 40000, 1500
+    io = torch.zeros(B, P, 7)
+    for b in range(B):
+        io[b, :, :5] = helpers.gen_boxes(P, 70 + b, 608.0)
+    io[..., 5] = torch.rand(B, P, generator=g)
+    io[..., 6] = 1.0
+    io[1, :, 5] *= 0.02                         # image with fewer candidates than the cap
+    io[1, :300, 5] = 0.6 + 0.3 * torch.rand(300, generator=g)
+    io[0, :50, 2] = 1.0                         # too small -> filtered
+    io[0, 50:60, 0] = float("nan")              # non-finite -> filtered
+    io[2, :, 5] = 0.001                         # nothing above the threshold
+    io = io.to(dev)
+    dets, counts = detect_select(io, 0.5, cap)
+    res = detect_postprocess(io, 0.5, 0.4, cap)
+    for b in range(B):
+        cand = nms_filter(io[b].clone(), 0.5, 2.0)                       # [n, 8] in input order
+        n_valid = len(cand)
+        n_sel = int(counts[b])
+        assert n_sel >= min(cap, n_valid) and n_sel <= min(n_valid, dets.shape[1])
+        if n_valid == 0:
+            assert int(res["num_keep"][b]) == 0
+            continue
+        top = torch.argsort(cand[:, 5], descending=True, stable=True)[:cap]
+        # the selection is a superset of the top-cap set, in input order
+        sel = dets[b, :n_sel]
+        thr_conf = float(cand[top[-1], 5])
+        assert float(sel[:, 5].min()) <= thr_conf and bool((sel[:, 5] > 0.5).all())
+        assert int((sel[:, 5] >= thr_conf).sum()) >= len(top)
+        # same final detections as the per-image pipeline
+        top_sorted = torch.sort(top).values
+        want_boxes = cand[top_sorted][:, :6]
+        want = want_boxes[pkg.r_nms(want_boxes.contiguous(), 0.4)]
+        got = res["dets"][b][res["keep"][b, :int(res["num_keep"][b])]]
+        assert got.shape == want.shape, (b, got.shape, want.shape)
+        assert torch.equal(got, want)
