@@ -298,6 +298,12 @@ int ryolo_space_to_depth(const void* x, int x_cstride, int batch, int h, int w, 
                          int xs_cstride, void* stream);
 int ryolo_depth_to_space(const void* dxs, int dxs_cstride, int batch, int h, int w, int c, void* gx,
                          int gx_cstride, int accumulate, void* stream);
+/* Squeeze-and-excitation block (reference SELayer, model/models.py:16-31; `[se]` blocks of cfg/ICDAR/yolov3_608_se.cfg,
+ * cfg/HRSC+/yolov3_512_se.cfg): x[b,:,:,c] *= sigmoid(W2 . relu(W1 . mean_hw x[b]))[c], in place on a padded-NHWC bf16
+ * tensor.  w1 [reduced, c], w2 [c, reduced] fp32 (nn.Linear weights, no bias); sums_scratch / scale_scratch [batch*c]
+ * fp32.  Eval path. */
+int ryolo_se_block(void* x, int x_cstride, int batch, int h, int w, int c, const float* w1, const float* w2,
+                   int reduced, float* sums_scratch, float* scale_scratch, void* stream);
 /* 2x2 max pooling of a padded-NHWC bf16 tensor (reference: the maxpool blocks of
  * cfg/yolov3-tiny.cfg, model/models.py:79-87).  stride 2: [in_h/2, in_w/2] output; stride 1: same
  * size, the window past the right/bottom edge reads the zero halo exactly like the reference's

@@ -71,6 +71,7 @@ SIGNATURES = {
     "ryolo_zero_insert2x": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "ryolo_space_to_depth": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "ryolo_depth_to_space": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "ryolo_se_block": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "ryolo_maxpool2x2": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "ryolo_nchw_to_padded": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "ryolo_im2col_first": (_i, [_vp, _i, _i, _i, _vp, _vp]),

@@ -87,16 +87,26 @@ __global__ void __launch_bounds__(BNT) bn_stats_kernel(const __nv_bfloat16* __re
   float s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; e++) s1[e] = s2[e] = 0.f;
+  constexpr int U = 4;   // independent 16-byte loads in flight per thread (a dependent load->add chain reaches ~55 % of HBM)
   for (int row = row_begin; row < row_end; row++) {
     const int b = row / g.h, y = row - b * g.h;
     const __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, zcs) + rs.cg * 8;
-    for (int x = rs.px0; x < g.w; x += rs.pstep) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(zr + (size_t)x * zcs), f);
+    for (int x0 = rs.px0; x0 < g.w; x0 += U * rs.pstep) {
+      uint4 v[U];
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        s1[e] += f[e];
-        s2[e] = fmaf(f[e], f[e], s2[e]);
+      for (int u = 0; u < U; u++) {
+        const int x = x0 + u * rs.pstep;
+        v[u] = x < g.w ? __ldg(reinterpret_cast<const uint4*>(zr + (size_t)x * zcs)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          s1[e] += f[e];
+          s2[e] = fmaf(f[e], f[e], s2[e]);
+        }
       }
     }
   }
@@ -193,24 +203,49 @@ __global__ void __launch_bounds__(BNT) bn_act_bwd_reduce_kernel(const __nv_bfloa
   float a1[8], a2[8], asl = 0.f;
 #pragma unroll
   for (int e = 0; e < 8; e++) a1[e] = a2[e] = 0.f;
+  constexpr int U = 2;   // pixels per iteration: both tensors' loads of both pixels are issued before any arithmetic
   for (int row = row_begin; row < row_end; row++) {
     const int b = row / g.h, y = row - b * g.h;
     const __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, zcs) + rs.cg * 8;
-    for (int x = rs.px0; x < g.w; x += rs.pstep) {
-      float f[8], d[8];
-      unpack8(*reinterpret_cast<const uint4*>(zr + (size_t)x * zcs), f);
-      load_dy(dy, dcs, g, b, y, x, rs.cg, up, d);
+    const __nv_bfloat16* dr = dy + pad_off(b, y, 0, g.h, g.w, dcs) + rs.cg * 8;
+    for (int x0 = rs.px0; x0 < g.w; x0 += U * rs.pstep) {
+      uint4 zv[U], dv[U];
+      float d[U][8];
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const float u = fmaf(f[e], sc[e], sh[e]);
-        float du = d[e];
-        if (has_act && !(u > 0.f)) {
-          asl = fmaf(d[e], u, asl);
-          du *= slope;
+      for (int q = 0; q < U; q++) {
+        const int x = x0 + q * rs.pstep;
+        const bool live = x < g.w;
+        zv[q] = live ? __ldg(reinterpret_cast<const uint4*>(zr + (size_t)x * zcs)) : make_uint4(0, 0, 0, 0);
+        if (!up) dv[q] = live ? __ldg(reinterpret_cast<const uint4*>(dr + (size_t)x * dcs)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < U; q++) {
+        const int x = x0 + q * rs.pstep;
+        if (!up) {
+          unpack8(dv[q], d[q]);
+        } else if (x < g.w) {
+          load_dy(dy, dcs, g, b, y, x, rs.cg, up, d[q]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e++) d[q][e] = 0.f;
         }
-        const float zh = (f[e] - mu[e]) * is[e];
-        a1[e] += du;
-        a2[e] = fmaf(du, zh, a2[e]);
+      }
+#pragma unroll
+      for (int q = 0; q < U; q++) {
+        float f[8];
+        unpack8(zv[q], f);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {       // dead pixels carry dy = 0: they add nothing to any sum
+          const float u = fmaf(f[e], sc[e], sh[e]);
+          float du = d[q][e];
+          if (has_act && !(u > 0.f)) {
+            asl = fmaf(d[q][e], u, asl);
+            du *= slope;
+          }
+          const float zh = (f[e] - mu[e]) * is[e];
+          a1[e] += du;
+          a2[e] = fmaf(du, zh, a2[e]);
+        }
       }
     }
   }
@@ -251,37 +286,53 @@ __global__ void __launch_bounds__(BNT) bn_act_bwd_apply_kernel(const __nv_bfloat
   }
   const int nrows = g.batch * g.h;
   const int row_begin = blockIdx.x * rows_per_block, row_end = min(nrows, row_begin + rows_per_block);
+  constexpr int U = 2;   // pixels per iteration, all loads issued before the arithmetic
   for (int row = row_begin; row < row_end; row++) {
     const int b = row / g.h, y = row - b * g.h;
     __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, zcs) + rs.cg * 8;
+    const __nv_bfloat16* dr = dy + pad_off(b, y, 0, g.h, g.w, dcs) + rs.cg * 8;
     __nv_bfloat16* gr = gres ? gres + pad_off(b, y, 0, g.h, g.w, gcs) + rs.cg * 8 : nullptr;
-    for (int x = rs.px0; x < g.w; x += rs.pstep) {
-      float f[8], d[8];
-      __nv_bfloat16* zp = zr + (size_t)x * zcs;
-      unpack8(*reinterpret_cast<const uint4*>(zp), f);
-      load_dy(dy, dcs, g, b, y, x, rs.cg, up, d);
-      if (gr) {  // shortcut branch: d(residual) (+)= dy   (never combined with upsample)
-        __nv_bfloat16* gp = gr + (size_t)x * gcs;
-        float o[8];
-        if (gres_acc) {
-          unpack8(*reinterpret_cast<const uint4*>(gp), o);
+    for (int x0 = rs.px0; x0 < g.w; x0 += U * rs.pstep) {
+      uint4 zv[U], dv[U], gv[U];
+      float d[U][8];
 #pragma unroll
-          for (int e = 0; e < 8; e++) o[e] += d[e];
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; e++) o[e] = d[e];
+      for (int q = 0; q < U; q++) {
+        const int x = x0 + q * rs.pstep;
+        if (x < g.w) {
+          zv[q] = *reinterpret_cast<const uint4*>(zr + (size_t)x * zcs);
+          if (!up) dv[q] = __ldg(reinterpret_cast<const uint4*>(dr + (size_t)x * dcs));
+          if (gr && gres_acc) gv[q] = *reinterpret_cast<const uint4*>(gr + (size_t)x * gcs);
         }
-        *reinterpret_cast<uint4*>(gp) = pack8(o);
       }
-      float out[8];
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const float u = fmaf(f[e], sc[e], sh[e]);
-        float du = d[e];
-        if (has_act && !(u > 0.f)) du *= slope;
-        out[e] = has_bn ? sc[e] * (du - m1[e] - (f[e] - mu[e]) * is[e] * m2[e]) : du;
+      for (int q = 0; q < U; q++) {
+        const int x = x0 + q * rs.pstep;
+        if (x >= g.w) continue;
+        if (!up) unpack8(dv[q], d[q]);
+        else load_dy(dy, dcs, g, b, y, x, rs.cg, up, d[q]);
+        if (gr) {  // shortcut branch: d(residual) (+)= dy   (never combined with upsample)
+          float o[8];
+          if (gres_acc) {
+            unpack8(gv[q], o);
+#pragma unroll
+            for (int e = 0; e < 8; e++) o[e] += d[q][e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) o[e] = d[q][e];
+          }
+          *reinterpret_cast<uint4*>(gr + (size_t)x * gcs) = pack8(o);
+        }
+        float f[8], out[8];
+        unpack8(zv[q], f);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const float u = fmaf(f[e], sc[e], sh[e]);
+          float du = d[q][e];
+          if (has_act && !(u > 0.f)) du *= slope;
+          out[e] = has_bn ? sc[e] * (du - m1[e] - (f[e] - mu[e]) * is[e] * m2[e]) : du;
+        }
+        *reinterpret_cast<uint4*>(zr + (size_t)x * zcs) = pack8(out);
       }
-      *reinterpret_cast<uint4*>(zp) = pack8(out);
     }
   }
 }

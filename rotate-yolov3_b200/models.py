@@ -25,6 +25,20 @@ from . import layout as L
 from .parse_config import parse_model_cfg
 
 
+class SELayer(nn.Module):
+    """reference model/models.py:16-31 (same parameter names: fc.0.weight [c/r, c], fc.2.weight [c, c/r]); executed by
+    ryolo_se_block inside the eval plan, this forward exists only for module-tree parity."""
+
+    def __init__(self, channel, reduction=16):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(nn.Linear(channel, channel // reduction, bias=False), nn.ReLU(inplace=True),
+                                nn.Linear(channel // reduction, channel, bias=False), nn.Sigmoid())
+
+    def forward(self, x):
+        raise RuntimeError("SELayer runs inside Darknet's fused plan (libryolo.so), not as a stand-alone module")
+
+
 class YOLOLayer(nn.Module):
     """reference model/models.py:170-227; decode runs in ryolo_yolo_decode."""
 
@@ -117,6 +131,8 @@ def create_modules(module_defs, arc, hyp):
                 modules = mp
         elif t == "upsample":
             modules = nn.Upsample(scale_factor=int(mdef["stride"]), mode="nearest")
+        elif t == "se":
+            modules = SELayer(int(mdef["channels"]))           # reference models.py:88-90
         elif t == "route":
             layers = [int(x) for x in mdef["layers"].split(",")]
             filters = sum(output_filters[l + 1 if l > 0 else l] for l in layers)
@@ -247,9 +263,7 @@ class Darknet(nn.Module):
                 ls = [l if l > 0 else i + l for l in ls]
                 c = sum(shape[l][0] for l in ls)
                 h, w = shape[ls[0]][1], shape[ls[0]][2]
-            elif t == "shortcut":
-                pass
-            elif t == "yolo":
+            elif t in ("shortcut", "yolo", "se"):
                 pass
             else:
                 raise NotImplementedError("block type %r has no sm_100a kernel yet" % t)
@@ -359,6 +373,21 @@ class Darknet(nn.Module):
                                            keep=(src, res, views[mat] if not is_head else out))))
                 i += 2 if (fuse_res or fuse_up) else 1
                 continue
+            if t == "se":
+                # squeeze-and-excitation rescales the previous block's output IN PLACE; legal when nothing else reads the
+                # unscaled tensor (the reference's graphs: [se] directly follows the down-sampling conv)
+                src = views[i - 1]
+                if src is None or (i - 1) in self.routes or src.c != int(d["channels"]):
+                    raise NotImplementedError("[se] block whose input is routed elsewhere / channel mismatch")
+                fc = self.module_list[i].fc
+                steps.append(("se", dict(x=src.ptr, xcs=src.cs, h=src.h, w=src.w, c=src.c,
+                                         w1=fc[0].weight.detach().float().contiguous(),
+                                         w2=fc[2].weight.detach().float().contiguous(), cr=fc[0].weight.shape[0],
+                                         sums=torch.zeros(batch * src.c, dtype=torch.float32, device=device),
+                                         scale=torch.zeros(batch * src.c, dtype=torch.float32, device=device), keep=src)))
+                views[i] = src
+                i += 1
+                continue
             if t == "maxpool":
                 src = views[i - 1]
                 v = out_view(i)
@@ -442,6 +471,10 @@ class Darknet(nn.Module):
                 st = lib.ryolo_maxpool2x2(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"], a["stride"],
                                           ctypes.c_void_p(a["y"]), a["ycs"], stream)
                 _lib.check(st, "ryolo_maxpool2x2")
+            elif kind == "se":
+                st = lib.ryolo_se_block(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"], _lib.ptr(a["w1"]),
+                                        _lib.ptr(a["w2"]), a["cr"], _lib.ptr(a["sums"]), _lib.ptr(a["scale"]), stream)
+                _lib.check(st, "ryolo_se_block")
             elif kind == "s2d":
                 st = lib.ryolo_space_to_depth(ctypes.c_void_p(a["x"]), a["xcs"], b, a["h"], a["w"], a["c"],
                                               _lib.ptr(a["xs"]), a["xs"].shape[-1], stream)

@@ -130,6 +130,13 @@ def non_max_suppression(prediction, conf_thres=0.5, nms_thres=0.5):
         if len(cand) == 0:
             continue
         cand = cand[(-cand[:, 5]).argsort()]
+        if pred.shape[1] == 7:
+            # single-class configs (every cfg the reference ships): class_pred is 0 for every row, so the per-class loop,
+            # its unique() (a host sync), the boolean masks and both re-sorts are identities -- r_nms returns ascending
+            # indices into the confidence-sorted rows, i.e. the result is already in the reference's final order
+            inds = r_nms(cand[:, :6], nms_thres)
+            output[image_i] = cand[inds]
+            continue
         det_max = []
         for c in cand[:, -1].unique():
             dc = cand[cand[:, -1] == c]

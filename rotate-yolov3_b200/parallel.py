@@ -124,6 +124,7 @@ class DistributedDataParallel(torch.nn.Module):
         self.module = module
         module._ddp = {"bucket_bytes": int(bucket_mb) << 20, "group": process_group}
         module._tplan = None          # the plan builds its buckets at construction
+        module._pplan = None
 
     def forward(self, *a, **k):
         return self.module(*a, **k)

@@ -188,12 +188,12 @@ class ParityPlan:
                                    dtype=torch.uint8, device=device)
                 b.pw_ver = None
                 if train:
-                    b.dz = _split_buf(batch, b.oh, b.ow, b.po, device)
                     b.bsums = torch.zeros(2 * b.cout + 1, dtype=torch.float64, device=device)
-                    # wgrad over both planes of dz and of the WHOLE source buffer (a slice of a concat buffer is picked
+                    # wgrad over all planes of dz and of the WHOLE source buffer (a slice of a concat buffer is picked
                     # out by px_unpack_wgrad's cin_off)
                     b.xw_buf = b.xs if b.s2d else b.src.buf
-                    b.dw = torch.zeros((b.k_eff * b.k_eff, NP * b.po, b.xw_buf.shape[-1]), dtype=torch.float32, device=device)
+                    b.dz_shape = (batch, b.oh + 2, b.ow + 2, NP * b.po)
+                    b.dw_shape = (b.k_eff * b.k_eff, NP * b.po, b.xw_buf.shape[-1])
                     if i > 0:
                         b.pwd = torch.empty(_lib.lib.ryolo_px_packed_weight_bytes(b.cin_eff, b.cout, b.k_eff, NTERMS),
                                             dtype=torch.uint8, device=device)
@@ -210,6 +210,23 @@ class ParityPlan:
         self.blocks = blocks
         self.heads = [b for b in blocks if b.is_head]
         if train:
+            # dz (split gradient of a block's raw conv output) and dw (plane blocks of the weight gradient) live only
+            # inside their own block's backward: ONE scratch of the largest size each, re-viewed per block (a per-block
+            # allocation costs 34 GB at batch 64).  Head blocks keep their own dz: all head gradients arrive before the
+            # first block runs.
+            import math
+            dz_max = max(math.prod(b.dz_shape) for b in blocks if not b.is_head)
+            dw_max = max(math.prod(b.dw_shape) for b in blocks)
+            self._dz_scratch = torch.zeros(dz_max, dtype=torch.bfloat16, device=device)
+            self._dw_scratch = torch.zeros(dw_max, dtype=torch.float32, device=device)
+            for b in blocks:
+                if b.is_head:
+                    b.dz = torch.zeros(b.dz_shape, dtype=torch.bfloat16, device=device)
+                    b.dz_shared = False
+                else:
+                    b.dz = self._dz_scratch[:math.prod(b.dz_shape)].view(b.dz_shape)
+                    b.dz_shared = True
+                b.dw = self._dw_scratch[:math.prod(b.dw_shape)].view(b.dw_shape)
             written = {}
 
             def claim(view):
@@ -302,6 +319,7 @@ class ParityPlan:
         for b in reversed(self.blocks):
             seq = m.module_list[b.i]
             if not b.is_head:
+                b.dz.zero_()            # shared scratch: the previous block's data would sit in this block's halo
                 _lib.check(lib.ryolo_px_bn_act_bwd(vp(b.gy.ptr), b.gy.cs, int(b.fuse_up), _lib.ptr(b.z), b.po, B, b.oh, b.ow,
                                                    b.cout, _lib.ptr(b.scale), _lib.ptr(b.shift), _lib.ptr(b.mean),
                                                    _lib.ptr(b.invstd), vp(b.slope_dev), 1, _lib.ptr(b.bsums), _lib.ptr(b.dz),
@@ -378,4 +396,16 @@ class DarknetParityFn(torch.autograd.Function):
         for name in ctx.names:
             parts = name.split(".")
             out.append(pg.get((int(parts[1]), parts[2] + "." + parts[3])))
+        ddp = getattr(m, "_ddp", None)
+        if ddp is not None:
+            # data-parallel replicas (parallel.DistributedDataParallel): average the gradients over the ranks.  One flat
+            # all-reduce after backward -- this path is the precision reference, not the throughput mode.
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(ddp["group"]) > 1:
+                have = [g for g in out if g is not None]
+                flat = torch._utils._flatten_dense_tensors(have)
+                dist.all_reduce(flat, group=ddp["group"])
+                flat.div_(dist.get_world_size(ddp["group"]))
+                it = iter(torch._utils._unflatten_dense_tensors(flat, have))
+                out = [next(it) if g is not None else None for g in out]
         return (None, None, None) + tuple(out)

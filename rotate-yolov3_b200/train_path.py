@@ -267,6 +267,10 @@ class TrainPlan:
 
     def _forward_body(self, x):
         m = self.model
+        if any(p.dtype != torch.float32 for p in m.parameters()):
+            # .half() models are supported in eval mode (weights are re-packed to bf16 anyway); the fused training step
+            # reads and updates fp32 master parameters in place, like apex O1 keeps them (train.py:165-166)
+            raise RuntimeError("Darknet training step needs fp32 parameters (call .float(); .half() is an inference option)")
         lib = _lib.lib
         st = _lib.stream_ptr(self.device)
         _lib.check(lib.ryolo_im2col_first(_lib.ptr(x), self.batch, self.h, self.w, _lib.ptr(self.col), st), "im2col")

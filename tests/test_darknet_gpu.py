@@ -133,3 +133,65 @@ def test_eval_plan_follows_in_place_weight_updates():
         m.module_list[0].Conv2d.weight.mul_(1.5)          # in place, still in eval mode
         io2 = m(x)[0].clone()
     assert not torch.allclose(io0, io2)
+
+
+def test_se_block_kernel_and_graph_vs_torch():
+    """[se] blocks (reference SELayer, model/models.py:16-31, cfg/ICDAR/yolov3_608_se.cfg): the in-place kernel against
+    x * sigmoid(W2 relu(W1 mean(x))) on the same bf16 tensor (one bf16 ulp), and a graph with an [se] block after its
+    down-sampling conv against a torch fp32 walk of the same modules (bf16 tolerance of the throughput mode)."""
+    import rotate_yolov3_b200 as pkg
+    from rotate_yolov3_b200 import layout as L
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(4)
+    b, c, h, w, cr = 3, 64, 13, 17, 4
+    x = torch.randn(b, c, h, w, generator=g).to(dev).to(torch.bfloat16).float()
+    w1 = (torch.randn(cr, c, generator=g) / 8).to(dev)
+    w2 = (torch.randn(c, cr, generator=g) / 2).to(dev)
+    buf = L.to_padded_nhwc(x, 64)
+    sums = torch.zeros(b * c, device=dev)
+    scale = torch.zeros(b * c, device=dev)
+    st = pkg._lib.lib.ryolo_se_block(pkg._lib.ptr(buf), 64, b, h, w, c, pkg._lib.ptr(w1), pkg._lib.ptr(w2), cr,
+                                     pkg._lib.ptr(sums), pkg._lib.ptr(scale), pkg._lib.stream_ptr(dev))
+    assert st == 0, pkg._lib.last_error()
+    s_want = torch.sigmoid(torch.relu(x.mean((2, 3)) @ w1.t()) @ w2.t())
+    assert torch.allclose(scale.view(b, c), s_want, rtol=1e-5, atol=1e-6)
+    want = x * s_want[:, :, None, None]
+    got = L.from_padded_nhwc(buf, c)
+    assert bool(((got - want).abs() <= 2.0 ** -8 * want.abs() + 1e-6).all())
+    assert float(buf[:, 0].abs().max()) == 0 and float(buf[:, :, 0].abs().max()) == 0          # halo untouched
+
+    def conv(f, k, s=1):
+        return "[convolutional]\nbatch_normalize=1\nfilters=%d\nsize=%d\nstride=%d\npad=1\nactivation=leaky\n\n" % (f, k, s)
+    cfg = ("[net]\nwidth=64\nheight=48\nchannels=3\n\n" + conv(32, 3) + conv(64, 3, 2) + "[se]\nchannels=64\n\n" + conv(32, 1) +
+           conv(64, 3) + "[shortcut]\nfrom=-3\nactivation=linear\n\n" +
+           "[convolutional]\nfilters=14\nsize=1\nstride=1\npad=1\nactivation=linear\n\n"
+           "[yolo]\nmask = 0-1\nanchors = ara 900 / 5.0 / -45, 45\nclasses=1\nnum=2\n\n")
+    m = pkg.Darknet(cfg, {"context_factor": 1.0})
+    init_darknet_weights(m, seed=5)
+    assert "module_list.2.fc.0.weight" in m.state_dict() and "module_list.2.fc.2.weight" in m.state_dict()
+    m = m.to(dev).eval()
+    xin = torch.rand(2, 3, 48, 64, generator=g).to(dev)
+    with torch.no_grad():
+        io, ps = m(xin)
+        # torch fp32 walk of the same modules
+        outs, t = [], xin
+        for i, (d, mod) in enumerate(zip(m.module_defs, m.module_list)):
+            ty = d["type"]
+            if ty == "convolutional":
+                wt, sc, bias, slope = m._folded(i, dev)
+                wt = wt * sc.view(-1, 1, 1, 1) if sc is not None else wt
+                t = F.conv2d(t, wt, bias, stride=int(d["stride"]), padding=(wt.shape[-1] - 1) // 2)
+                if slope is not None:
+                    t = torch.where(t > 0, t, slope * t)
+            elif ty == "se":
+                s_ = torch.sigmoid(torch.relu(t.mean((2, 3)) @ mod.fc[0].weight.t()) @ mod.fc[2].weight.t())
+                t = t * s_[:, :, None, None]
+            elif ty == "shortcut":
+                t = t + outs[i + int(d["from"])]
+            elif ty == "yolo":
+                head = t
+            outs.append(t)
+    layer = m.module_list[m.yolo_layers[0]]
+    want = head.view(2, layer.na, 7, head.shape[2], head.shape[3]).permute(0, 1, 3, 4, 2)
+    err = (ps[0] - want).abs()
+    assert float(err.max()) <= 3e-2 * float(want.abs().max()), float(err.max())
