@@ -278,9 +278,13 @@ def cpu_train(steps=1, batch=2):
     model.nc, model.hyp = 1, dict(TRAIN_HYP)
     x = torch.rand(batch, 3, 608, 608)
     tg = make_targets(batch, 5)
+    pg_w = [p for n, p in model.named_parameters() if "Conv2d.weight" in n]
+    pg_o = [p for n, p in model.named_parameters() if "Conv2d.weight" not in n]
+    opt = torch.optim.SGD([{"params": pg_o}, {"params": pg_w, "weight_decay": 4.569e-4}], lr=1e-4, momentum=0.97, nesterov=True)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
         ps = torch_port_forward(model, x, True)
         for p, yi in zip(ps, model.yolo_layers):
             layer = model.module_list[yi]
@@ -288,11 +292,10 @@ def cpu_train(steps=1, batch=2):
                 layer.create_grids((608, 608), (p.shape[3], p.shape[2]), "cpu", torch.float32)
         loss, _ = compute_loss(ps, tg.clone(), model, model.hyp)
         loss.backward()
+        opt.step()
         times.append(time.perf_counter() - t0)
-        for p in model.parameters():
-            p.grad = None
     return cb_finish({"value": batch / min(times), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                      "sample": "%d images 608x608 per step: forward + compute_loss + backward of THIS REPO's Darknet module "
+                      "sample": "%d images 608x608 per step: forward + compute_loss + backward + SGD step of THIS REPO's Darknet module "
                                 "tree and loss restatement executed by stock PyTorch CPU kernels (not the reference model: "
                                 "/root/reference does not exist on the GPU box; same graph, same fp32 nn ops)" % batch}), times
 

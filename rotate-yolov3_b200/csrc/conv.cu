@@ -139,27 +139,49 @@ struct ConvParams {
 
 // NBUF = group buffers per epilogue team.  2 lets a residual group prefetch while the other buffer is processed; the
 // BN = 256 tile only has room for 4 pipeline stages with NBUF = 1, which is what its residual-free launches use.
-template <int BN, int NBUF>
+//
+// AROW ("one A load per kernel row").  The taps of one kernel row (dx = -1, 0, +1) read the SAME pixels shifted by one
+// row of the flat pixel index, i.e. by one 128-byte line of the swizzled tile.  With AROW the producer loads ONE box of
+// BM + 8 rows per (kernel row, k-chunk) and the MMA issuer addresses tap dx through a descriptor whose start is shifted
+// by dx lines (matrix base offset = dx: the start is no longer aligned to the 1024-byte swizzle pattern) -- a third of
+// the A traffic.  Measured motivation: every 3x3 layer moved ~36-54 B/clk/SM from L2, at or beyond the ~42 B/clk/SM the
+// LTS can deliver to 148 SMs (B300_MICROARCH.md: ~6300 B/cyc chip-wide): the kernel was L2-throughput bound.  A and B
+// then live in separate rings (A stage = 18 KB every 3 taps, B stage = BN x 128 B every tap).
+//
+// BRES ("resident weights", thin layers).  With cout <= 64 there is ONE n-tile, so every tile of the CTA multiplies by the
+// same <= 72 KB of packed weights; after AROW the per-tile weight re-load (9 x 8 KB) was the larger half of the L2 traffic
+// of those layers.  With BRES the producer loads all (tap, k-chunk) weight blocks once per CTA into a resident region and
+// the ring carries A only.
+template <int BN, int NBUF, bool AROW, bool BRES = false>
 struct ConvSmem {
-  static constexpr int kStages = (BN == 256) ? (NBUF == 1 ? 4 : 3) : (BN == 128 ? 5 : 6);
+  static constexpr int kStages = (BN == 256) ? (NBUF == 1 ? 4 : 3) : (BN == 128 ? 5 : 6);   // !AROW: (A, B) pairs
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTileBytes = kStages * kStageBytes;
+  // AROW rings
+  static constexpr int kARowRows = BM + 8;
+  static constexpr int kARowTx = kARowRows * 128;            // bytes one A-row box delivers
+  static constexpr int kARowBytes = 18 * 1024;               // stage pitch (1024-byte aligned)
+  static constexpr int kAStages = 3;
+  static constexpr int kBStages = BRES ? 9 : ((BN == 256) ? (NBUF == 1 ? 4 : 3) : (BN == 128 ? 6 : 8));   // BRES: 9 resident blocks
+  static constexpr int kTileBytes = AROW ? kAStages * kARowBytes + kBStages * kBBytes : kStages * kStageBytes;
+  static constexpr int kBRingOffset = kAStages * kARowBytes;
   static constexpr int kGroupBytes = BM * 128;                        // one [128 pixels x 64 filters] bf16 group
   static constexpr int kStagingOffset = kTileBytes;                   // [team][buffer] group buffers
   static constexpr int kBarOffset = kStagingOffset + 2 * NBUF * kGroupBytes;
-  // full[kStages], empty[kStages], tfull[2], tempty[2], rfull[4]
-  static constexpr int kNumBars = 2 * kStages + 8;
+  // !AROW: full[kStages], empty[kStages];  AROW: afull[3], aempty[3], bfull[kBStages], bempty[kBStages];  then tfull[2],
+  // tempty[2], rfull[4]
+  static constexpr int kPipeBars = AROW ? 2 * kAStages + 2 * kBStages : 2 * kStages;
+  static constexpr int kNumBars = kPipeBars + 8;
   static constexpr int kBiasOffset = kBarOffset + kNumBars * 8 + 16;  // [team][64] fp32: bias of the team's current group
   static constexpr int kTotal = kBiasOffset + 2 * 64 * 4 + 1024 /*alignment slack*/;
 };
 
-template <int BN, int NBUF>
+template <int BN, int NBUF, bool AROW, bool BRES = false>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_r, const ConvParams p) {
-  using S = ConvSmem<BN, NBUF>;
+  using S = ConvSmem<BN, NBUF, AROW, BRES>;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -167,9 +189,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t bar_base = smem_base + S::kBarOffset;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S::kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S::kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S::kStages + 2 + a); };
-  auto rfull_bar = [&](int i) { return bar_base + 8u * (2 * S::kStages + 4 + i); };
+  // AROW rings (same barrier block, different carving)
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (S::kAStages + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * S::kAStages + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (2 * S::kAStages + S::kBStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (S::kPipeBars + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (S::kPipeBars + 2 + a); };
+  auto rfull_bar = [&](int i) { return bar_base + 8u * (S::kPipeBars + 4 + i); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOffset + S::kNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -177,10 +204,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int k_iters = p.taps * p.kchunks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S::kStages; s++) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
+    for (int s = 0; s < S::kPipeBars; s++) mbar_init(bar_base + 8u * s, 1);
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 8);  // one arrive per epilogue warp
@@ -199,7 +223,94 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  // kernel-row decomposition of the taps (AROW): ky rows of kx taps; tap (dyi, dxi) has pixel offset
+  // (dyi + d0) * wp + (dxi + d0), d0 = -1 (3x3, 2x2) or 0 (2x2 flipped)
+  const int kx = p.taps == 9 ? 3 : 2, ky = kx;
+  const int d0 = p.tap_flip ? 0 : -1;
+  if (AROW && warp == 0) {
+    // ===================== TMA producer, separate A-row / B rings =====================
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      if (BRES) {
+        // all weight blocks of the (single) n-tile, once: block index = tap * kchunks + kc, completion on bfull[0]
+        const int nblk = p.taps * p.kchunks;
+        mbar_expect_tx(bfull_bar(0), nblk * S::kBBytes);
+        for (int blk = 0; blk < nblk; blk++)
+          tma_load_2d(smem_base + S::kBRingOffset + blk * S::kBBytes, &map_b, bfull_bar(0), (blk % p.kchunks) * BK,
+                      (blk / p.kchunks) * p.cout_pad);
+      }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        const int p0 = mt * BM;
+        for (int dyi = 0; dyi < ky; dyi++) {
+          for (int kc = 0; kc < p.kchunks; kc++) {
+            mbar_wait(aempty_bar(as), aph ^ 1);
+            mbar_expect_tx(afull_bar(as), S::kARowTx);
+            tma_load_2d(smem_base + as * S::kARowBytes, &map_a, afull_bar(as), kc * BK, p0 + (dyi + d0) * p.wp + d0);
+            if (++as == S::kAStages) { as = 0; aph ^= 1; }
+            if (BRES) continue;
+            for (int dxi = 0; dxi < kx; dxi++) {
+              mbar_wait(bempty_bar(bs), bph ^ 1);
+              mbar_expect_tx(bfull_bar(bs), S::kBBytes);
+              tma_load_2d(smem_base + S::kBRingOffset + bs * S::kBBytes, &map_b, bfull_bar(bs), kc * BK,
+                          (dyi * kx + dxi) * p.cout_pad + nt * BN);
+              if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (AROW && warp == 1) {
+    // ===================== MMA issuer, A-row form =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      if (BRES) {
+        mbar_wait(bfull_bar(0), 0);          // the resident weights have landed
+        tc_fence_after();
+      }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accum = 0;
+        for (int dyi = 0; dyi < ky; dyi++) {
+          for (int kc = 0; kc < p.kchunks; kc++) {
+            mbar_wait(afull_bar(as), aph);
+            tc_fence_after();
+            const uint32_t sa = smem_base + as * S::kARowBytes;
+            for (int dxi = 0; dxi < kx; dxi++) {
+              if (BRES) {
+                bs = (dyi * kx + dxi) * p.kchunks + kc;
+              } else {
+                mbar_wait(bfull_bar(bs), bph);
+                tc_fence_after();
+              }
+              // tap dxi = rows [dxi, dxi + 128) of the A-row box: start shifted by dxi 128-byte lines, and since that start
+              // is not aligned to the 1024-byte swizzle pattern any more, the descriptor's base offset says so
+              const uint64_t adesc = make_smem_desc(sa + dxi * 128) | ((uint64_t)dxi << 49);
+              const uint64_t bdesc = make_smem_desc(smem_base + S::kBRingOffset + bs * S::kBBytes);
+#pragma unroll
+              for (int k = 0; k < BK / 16; k++) {
+                tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                accum = 1;
+              }
+              if (!BRES) {
+                tc_commit(bempty_bar(bs));
+                if (++bs == S::kBStages) { bs = 0; bph ^= 1; }
+              }
+            }
+            tc_commit(aempty_bar(as));
+            if (++as == S::kAStages) { as = 0; aph ^= 1; }
+          }
+        }
+        tc_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -553,15 +664,16 @@ int encode_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t row
   return RYOLO_OK;
 }
 
-template <int BN, int NBUF>
+template <int BN, int NBUF, bool AROW, bool BRES = false>
 static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr,
                        const ConvParams& p, cudaStream_t stream) {
-  using S = ConvSmem<BN, NBUF>;
-  RYOLO_SMEM_OPT_IN((conv_igemm_kernel<BN, NBUF>), S::kTotal);
+  using S = ConvSmem<BN, NBUF, AROW, BRES>;
+  static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
+  RYOLO_SMEM_OPT_IN((conv_igemm_kernel<BN, NBUF, AROW, BRES>), S::kTotal);
   const int num_sms = device_sm_count();
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
-  conv_igemm_kernel<BN, NBUF><<<grid, CONV_THREADS, S::kTotal, stream>>>(ma, mb, mo, mr, p);
+  conv_igemm_kernel<BN, NBUF, AROW, BRES><<<grid, CONV_THREADS, S::kTotal, stream>>>(ma, mb, mo, mr, p);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }
@@ -672,9 +784,17 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   }
   p.dbg = dbg;
 
+  // A-row sharing (one A box per kernel row instead of one per tap) on every multi-tap launch: RYOLO_CONV_AROW=1; =2 adds
+  // resident weights on the thin (cout <= 64) layers; 0 = per-tap loads
+  static int arow_env = -1;
+  if (arow_env < 0) {
+    const char* e = getenv("RYOLO_CONV_AROW");
+    arow_env = e ? atoi(e) : 0;   // default off until the shifted-descriptor form is validated on hardware (profiles/)
+  }
+  const bool arow = arow_env != 0 && g.taps > 1 && dbg == 0;
   CUtensorMap ma, mb;
   const int a_inner = d->cin_stride < g.cin_pad ? d->cin_stride : g.cin_pad;
-  int st = encode_map_2d(&ma, x, (uint64_t)a_inner, (uint64_t)p.np, (uint64_t)d->cin_stride * 2, BK, BM);
+  int st = encode_map_2d(&ma, x, (uint64_t)a_inner, (uint64_t)p.np, (uint64_t)d->cin_stride * 2, BK, arow ? BM + 8 : BM);
   if (st != RYOLO_OK) return st;
   st = encode_map_2d(&mb, packed_w, (uint64_t)g.cin_pad, (uint64_t)g.taps * g.cout_pad, (uint64_t)g.cin_pad * 2, BK,
                      (uint32_t)g.bn);
@@ -694,11 +814,20 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
     st = encode_map_2d(&mr, residual, (uint64_t)d->cout, (uint64_t)p.np, (uint64_t)d->res_stride * 2, 64, BM);
     if (st != RYOLO_OK) return st;
   }
-  if (g.bn == 256) {
-    if (p.tma_store && p.has_res) return launch_conv<256, 2>(ma, mb, mo, mr, p, stream);
-    return launch_conv<256, 1>(ma, mb, mo, mr, p, stream);
+  if (arow) {
+    if (g.bn == 256) {
+      if (p.tma_store && p.has_res) return launch_conv<256, 2, true>(ma, mb, mo, mr, p, stream);
+      return launch_conv<256, 1, true>(ma, mb, mo, mr, p, stream);
+    }
+    if (g.bn == 128) return launch_conv<128, 2, true>(ma, mb, mo, mr, p, stream);
+    if (arow_env >= 2 && p.n_tiles == 1 && g.taps * p.kchunks <= 9) return launch_conv<64, 2, true, true>(ma, mb, mo, mr, p, stream);
+    return launch_conv<64, 2, true>(ma, mb, mo, mr, p, stream);
   }
-  if (g.bn == 128) return launch_conv<128, 2>(ma, mb, mo, mr, p, stream);
-  return launch_conv<64, 2>(ma, mb, mo, mr, p, stream);
+  if (g.bn == 256) {
+    if (p.tma_store && p.has_res) return launch_conv<256, 2, false>(ma, mb, mo, mr, p, stream);
+    return launch_conv<256, 1, false>(ma, mb, mo, mr, p, stream);
+  }
+  if (g.bn == 128) return launch_conv<128, 2, false>(ma, mb, mo, mr, p, stream);
+  return launch_conv<64, 2, false>(ma, mb, mo, mr, p, stream);
 }
 
