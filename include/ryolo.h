@@ -226,6 +226,26 @@ int ryolo_conv_pack_weights_ex(const ryolo_conv_desc* d, const float* weight, co
                                void* packed_out, int mode, void* stream);
 int ryolo_conv_unpack_wgrad(const float* dw, int cout_pad, int cin_pad, int mode, int cout, int cin,
                             int ksize, float* grad, void* stream);
+/* Multi-tensor forms (one launch for all layers of a training step; the per-layer launches are a fixed ~2 ms per step
+ * that caps strong scaling).  Job tables and prefix sums (prefix[j] = first global element of job j, prefix[njobs] =
+ * total) live in DEVICE memory and are built once per plan.  Pack: `packed` receives taps*cout_pad*cin_pad bf16 for the
+ * operand described like ryolo_conv_pack_weights_ex (ks = taps per side of the PACKED operand: 1, 3 or 2; cout/cin of
+ * the packed operand; mode 0..3).  Unpack: `grad` receives cout*cin*ks*ks fp32 in nn.Conv2d layout (mode 0 / 2 as
+ * ryolo_conv_unpack_wgrad; ks = kernel size of the nn.Conv2d weight). */
+typedef struct ryolo_pack_job {
+  const float* weight;
+  void* packed;
+  int32_t cout, cin, ks, cout_pad, cin_pad, mode;
+} ryolo_pack_job;
+typedef struct ryolo_unpack_job {
+  const float* dw;
+  float* grad;
+  int32_t cout_pad, cin_pad, mode, cout, cin, ks;
+} ryolo_unpack_job;
+int ryolo_conv_pack_weights_multi(const ryolo_pack_job* jobs_dev, int njobs, const long long* prefix_dev,
+                                  long long total, void* stream);
+int ryolo_conv_unpack_wgrad_multi(const ryolo_unpack_job* jobs_dev, int njobs, const long long* prefix_dev,
+                                  long long total, void* stream);
 /* y = act(conv(x, W') + bias) [+ residual].  bias: fp32 [cout_pad] (zero beyond cout). */
 size_t ryolo_conv_workspace_bytes(const ryolo_conv_desc* d);
 int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, const void* packed_w,

@@ -34,6 +34,18 @@ class ConvDesc(ctypes.Structure):
                 ("res_stride", ctypes.c_int32), ("upsample2x", ctypes.c_int32), ("out_dtype", ctypes.c_int32)]
 
 
+class PackJob(ctypes.Structure):
+    """mirror of ryolo_pack_job"""
+    _fields_ = [("weight", ctypes.c_void_p), ("packed", ctypes.c_void_p), ("cout", ctypes.c_int32), ("cin", ctypes.c_int32),
+                ("ks", ctypes.c_int32), ("cout_pad", ctypes.c_int32), ("cin_pad", ctypes.c_int32), ("mode", ctypes.c_int32)]
+
+
+class UnpackJob(ctypes.Structure):
+    """mirror of ryolo_unpack_job"""
+    _fields_ = [("dw", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("cout_pad", ctypes.c_int32), ("cin_pad", ctypes.c_int32),
+                ("mode", ctypes.c_int32), ("cout", ctypes.c_int32), ("cin", ctypes.c_int32), ("ks", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol include/ryolo.h declares (tests/test_abi.py checks it)
 SIGNATURES = {
     "ryolo_abi_version": (_i, []),
@@ -58,6 +70,8 @@ SIGNATURES = {
     "ryolo_conv_pack_weights": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "ryolo_conv_pack_weights_ex": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _i, _vp]),
     "ryolo_conv_unpack_wgrad": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ryolo_conv_pack_weights_multi": (_i, [_vp, _i, _vp, ctypes.c_longlong, _vp]),
+    "ryolo_conv_unpack_wgrad_multi": (_i, [_vp, _i, _vp, ctypes.c_longlong, _vp]),
     "ryolo_conv_workspace_bytes": (_sz, [ctypes.POINTER(ConvDesc)]),
     "ryolo_conv_bn_act_fwd": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ryolo_conv_first_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _f, _vp, _i, _vp]),

@@ -156,7 +156,7 @@ class TrainPlan:
                         # dgrad: stride-1 conv of dz (at the INPUT resolution) with mirrored taps / transposed weights
                         blk.ddesc = L.make_desc(batch, blk.src.h, blk.src.w, blk.cout, blk.zcs, blk.cin, blk.gsrc.cs,
                                                 blk.k, 1, False, 0.0, False, blk.gsrc.cs, False, False)
-                blk.dw = torch.zeros((blk.k_eff * blk.k_eff, blk.cout_pad, blk.cin_pad), dtype=torch.float32, device=device)
+                blk.dw_shape = (blk.k_eff * blk.k_eff, blk.cout_pad, blk.cin_pad)
                 blk.pw = torch.empty(_lib.lib.ryolo_conv_packed_weight_bytes(ctypes.byref(blk.fdesc)), dtype=torch.uint8,
                                      device=device)
                 if i > 0:
@@ -187,6 +187,17 @@ class TrainPlan:
             blk.gres_acc = claim(blk.gres) if blk.gres is not None else False
             blk.gsrc_acc = claim(blk.gsrc) if blk.gsrc is not None else False
         self._build_arena()
+        # split-K partial sums of every layer's weight gradient in ONE buffer: one fill per step instead of 75
+        off = 0
+        for blk in blocks:
+            blk.dw_off = off
+            off += L.round_up(blk.dw_shape[0] * blk.dw_shape[1] * blk.dw_shape[2], 64)
+        self.dw_arena = torch.zeros(off, dtype=torch.float32, device=device)
+        for blk in blocks:
+            n_ = blk.dw_shape[0] * blk.dw_shape[1] * blk.dw_shape[2]
+            blk.dw = self.dw_arena[blk.dw_off:blk.dw_off + n_].view(blk.dw_shape)
+        self._key_now = None
+        self._multi = None           # job tables of the multi-tensor pack / unpack launches (keyed on parameter storage)
         self.gen = 0                 # forward generation: backward must see the activations of ITS forward
         self.consumed = True
         self.graphs = None           # CUDA graphs of forward / backward segments (model.use_cuda_graph)
@@ -265,6 +276,80 @@ class TrainPlan:
         """storage identity of everything the captured graphs point at"""
         return tuple(p.data_ptr() for p in self.model.parameters()) + tuple(b.data_ptr() for b in self.model.buffers())
 
+    # ---- multi-tensor pack / unpack (csrc/multi.cu): job tables in device memory, rebuilt when parameter storage moves ----
+    def _job_table(self, jobs, cls):
+        arr = (cls * len(jobs))(*jobs)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        sizes = []
+        for j in jobs:
+            if cls is _lib.PackJob:
+                sizes.append(j.ks * j.ks * j.cout_pad * j.cin_pad)
+            else:
+                sizes.append(j.cout * j.cin * j.ks * j.ks)
+        prefix = torch.tensor([0] + list(torch.tensor(sizes, dtype=torch.int64).cumsum(0).tolist()), dtype=torch.int64)
+        return raw, prefix.to(self.device), len(jobs), int(prefix[-1])
+
+    def _multi_tables(self):
+        key = self._key_now if self._key_now is not None else self._param_key()
+        if self._multi is not None and self._multi["key"] == key:
+            return self._multi
+        m = self.model
+
+        def pads(cout, cin):
+            bn_ = 256 if cout > 128 else (128 if cout > 64 else 64)
+            return L.round_up(cout, bn_), L.round_up(cin, 64)
+        pack = []
+        for blk in self.blocks:
+            w = m.module_list[blk.i].Conv2d.weight
+            if blk.i == 0:
+                cout, cin, ks, mode = blk.cout, 27, 1, 0                       # im2col form: [cout, 27, 1, 1]
+            elif blk.s2d:
+                cout, cin, ks, mode = blk.cout, blk.cin_eff, 2, 2
+            else:
+                cout, cin, ks, mode = blk.cout, blk.cin, blk.k_eff, 0
+            cp, kp = pads(cout, cin)
+            assert blk.pw.numel() == ks * ks * cp * kp * 2, (blk.i, blk.pw.numel(), ks, cp, kp)
+            pack.append(_lib.PackJob(w.data_ptr(), blk.pw.data_ptr(), cout, cin, ks, cp, kp, mode))
+            if blk.i > 0:                                                        # dgrad operand: mirrored taps, transposed
+                if blk.s2d:
+                    cout_d, cin_d, ks_d, mode_d = blk.cin_eff, blk.cout, 2, 3
+                else:
+                    cout_d, cin_d, ks_d, mode_d = blk.cin, blk.cout, blk.k, 1
+                cpd, kpd = pads(cout_d, cin_d)
+                assert blk.pwd.numel() == ks_d * ks_d * cpd * kpd * 2, (blk.i, blk.pwd.numel(), ks_d, cpd, kpd)
+                pack.append(_lib.PackJob(w.data_ptr(), blk.pwd.data_ptr(), cout_d, cin_d, ks_d, cpd, kpd, mode_d))
+        unpack = []
+        for seg in self.segments:
+            jobs = []
+            for blk in seg:
+                if blk.s2d:
+                    jobs.append(_lib.UnpackJob(blk.dw.data_ptr(), blk.gw.data_ptr(), blk.cout_pad, blk.cin_pad, 2, blk.cout,
+                                               blk.src.c, 3))
+                else:
+                    jobs.append(_lib.UnpackJob(blk.dw.data_ptr(), blk.gw.data_ptr(), blk.cout_pad, blk.cin_pad, 0, blk.cout,
+                                               blk.cin, blk.k_eff))
+            unpack.append(self._job_table(jobs, _lib.UnpackJob))
+        self._multi = {"key": key, "pack": self._job_table(pack, _lib.PackJob), "unpack": unpack}
+        return self._multi
+
+    def _pack_all(self):
+        """every forward AND dgrad weight operand of the step in one launch (the weights are constant within a step)"""
+        for b in self.blocks:
+            if self.model.module_list[b.i].Conv2d.weight.dtype != torch.float32:
+                raise RuntimeError("fp32 parameters required")
+        raw, prefix, n, total = self._multi_tables()["pack"]
+        _lib.check(_lib.lib.ryolo_conv_pack_weights_multi(_lib.ptr(raw), n, _lib.ptr(prefix), total, _lib.stream_ptr(self.device)),
+                   "pack_weights_multi")
+
+    def _backward_segment(self, si):
+        if si == 0:
+            self.dw_arena.zero_()
+        for blk in self.segments[si]:
+            self._backward_block(blk)
+        raw, prefix, n, total = self._multi_tables()["unpack"][si]
+        _lib.check(_lib.lib.ryolo_conv_unpack_wgrad_multi(_lib.ptr(raw), n, _lib.ptr(prefix), total,
+                                                          _lib.stream_ptr(self.device)), "unpack_wgrad_multi")
+
     def _forward_body(self, x):
         m = self.model
         if any(p.dtype != torch.float32 for p in m.parameters()):
@@ -276,6 +361,7 @@ class TrainPlan:
         _lib.check(lib.ryolo_im2col_first(_lib.ptr(x), self.batch, self.h, self.w, _lib.ptr(self.col), st), "im2col")
         n_per_pixel = float(self.batch)
         self._slopes()
+        self._pack_all()
         bn_counters = []
         for blk in self.blocks:
             seq = m.module_list[blk.i]
@@ -287,7 +373,6 @@ class TrainPlan:
                 _lib.check(lib.ryolo_space_to_depth(ctypes.c_void_p(blk.src.ptr), blk.src.cs, self.batch, blk.src.h, blk.src.w,
                                                     blk.src.c, _lib.ptr(blk.xs), blk.xs_cs, st), "s2d")
                 x_ptr = blk.xs.data_ptr()
-            L.pack_weights(blk.fdesc, w, None, 2 if blk.s2d else 0, out=blk.pw)
             if blk.is_head:
                 if getattr(blk, "bias_pad", None) is None:
                     blk.bias_pad = L.padded_bias(blk.fdesc, torch.zeros(blk.cout, device=self.device))
@@ -331,6 +416,7 @@ class TrainPlan:
             layer = m.module_list[yi]
             if (layer.nx, layer.ny) != (blk.ow, blk.oh):
                 layer.create_grids((self.h, self.w), (blk.ow, blk.oh), self.device, torch.float32)
+        self._key_now = self._param_key()      # once per step: storage identity of parameters / buffers
         if getattr(m, "use_cuda_graph", False):
             outs = self._forward_graph(x)
         else:
@@ -344,7 +430,7 @@ class TrainPlan:
     # rank) is the host, not the GPU.  Inputs are copied into static buffers; outputs are static buffers that the next
     # step overwrites (standard CUDA-graph semantics).
     def _forward_graph(self, x):
-        key = self._param_key()
+        key = self._key_now
         if self.graphs is None or self.graphs["key"] != key:
             self.graphs = {"key": key, "pool": None}
             self.x_static = x.clone()
@@ -391,15 +477,10 @@ class TrainPlan:
                                             ctypes.c_void_p(blk.slope_dev), st),
                        "bn_act_bwd")
             dz = blk.z
-        blk.dw.zero_()
-        w = seq.Conv2d.weight.detach()
         if blk.s2d:
             _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.zcs, blk.cout_pad, _lib.ptr(blk.xs), blk.xs_cs,
                                             blk.cin_pad, self.batch, blk.src.h // 2, blk.src.w // 2, 2, _lib.ptr(blk.dw),
                                             st), "wgrad s2d")
-            _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 2, blk.cout, blk.src.c, 3,
-                                                   _lib.ptr(blk.gw), st), "unpack wgrad s2d")
-            L.pack_weights(blk.ddesc, w, None, 3, out=blk.pwd)          # mirrored 2x2 taps, transposed, in the pack kernel
             _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(blk.pwd),
                                                  _lib.ptr(self.zero_bias), None, _lib.ptr(blk.dxs), None, 0, st), "dgrad s2d")
             _lib.check(lib.ryolo_depth_to_space(_lib.ptr(blk.dxs), blk.xs_cs, self.batch, blk.src.h, blk.src.w, blk.src.c,
@@ -412,12 +493,9 @@ class TrainPlan:
         _lib.check(lib.ryolo_conv_wgrad(_lib.ptr(dz), blk.zcs, blk.cout_pad, ctypes.c_void_p(blk.src.ptr), blk.src.cs,
                                         blk.cin_pad, self.batch, blk.src.h, blk.src.w, blk.k_eff, _lib.ptr(blk.dw), st),
                    "wgrad")
-        _lib.check(lib.ryolo_conv_unpack_wgrad(_lib.ptr(blk.dw), blk.cout_pad, blk.cin_pad, 0, blk.cout, blk.cin, blk.k_eff,
-                                               _lib.ptr(blk.gw), st), "unpack wgrad")
         if blk.i > 0:
             gp = blk.gsrc.ptr
             blk.ddesc.has_residual = int(blk.gsrc_acc)
-            L.pack_weights(blk.ddesc, w, None, 1, out=blk.pwd)          # taps mirrored + transposed in the pack kernel
             _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(blk.pwd),
                                                  _lib.ptr(self.zero_bias), ctypes.c_void_p(gp) if blk.gsrc_acc else None,
                                                  ctypes.c_void_p(gp), None, 0, st), "dgrad")
@@ -428,20 +506,18 @@ class TrainPlan:
         use_graph = getattr(m, "use_cuda_graph", False) and self.graphs is not None and "fwd" in self.graphs
         if use_graph and "bwd" not in self.graphs:
             # first backward after capture of the forward: run eagerly once (warm-up), then capture every segment
-            for seg in self.segments:
-                for blk in seg:
-                    self._backward_block(blk)
+            for si, seg in enumerate(self.segments):
+                self._backward_segment(si)
                 if self.buckets:
                     self.buckets.ready(seg[-1].arena_end)
             inv = self.buckets.finish() if self.buckets else 1.0
             out_flat = self.garena * inv
             torch.cuda.synchronize(self.device)
             gs = []
-            for seg in self.segments:
+            for si in range(len(self.segments)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=self.graphs["pool"]):
-                    for blk in seg:
-                        self._backward_block(blk)
+                    self._backward_segment(si)
                 gs.append(g)
             self.graphs["bwd"] = gs
             # the capture passes did not execute; the eager pass above produced this step's gradients
@@ -450,8 +526,7 @@ class TrainPlan:
                 if use_graph:
                     self.graphs["bwd"][si].replay()
                 else:
-                    for blk in seg:
-                        self._backward_block(blk)
+                    self._backward_segment(si)
                 if self.buckets:
                     self.buckets.ready(seg[-1].arena_end)     # NCCL all-reduce of the finished bucket on the side stream
             if self.time_comm:

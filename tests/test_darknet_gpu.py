@@ -37,8 +37,8 @@ def _emulate_bf16(model, x):
             w, scale, bias, slope = model._folded(i, x.device)
             wq = q(w * scale.view(-1, 1, 1, 1)) if scale is not None else q(w)
             xin = x if i == 0 else q(x)
-            if i == 0:
-                wq = w * scale.view(-1, 1, 1, 1)           # first layer runs in fp32 on the CUDA cores
+            # first layer (first.cu): tensor pipe with the image as bf16 hi + lo halves (16 mantissa bits: fp32 up to
+            # 2^-17) and bf16 weights like every other layer -- so only the weights are quantised here
             k = w.shape[-1]
             y = F.conv2d(xin, wq, bias, stride=int(d["stride"]), padding=(k - 1) // 2)
             if slope is not None:
@@ -195,3 +195,21 @@ def test_se_block_kernel_and_graph_vs_torch():
     want = head.view(2, layer.na, 7, head.shape[2], head.shape[3]).permute(0, 1, 3, 4, 2)
     err = (ps[0] - want).abs()
     assert float(err.max()) <= 3e-2 * float(want.abs().max()), float(err.max())
+
+
+def test_half_module_runs_the_eval_path():
+    """detect.py --half does model.half(): parameters become fp16.  The packed operands are bf16 anyway, so the eval
+    forward must accept it (fp32 outputs) and agree with the fp32-parameter model up to the fp16 rounding of the weights"""
+    m = _model()
+    x = torch.rand(2, 3, 64, 96, generator=torch.Generator().manual_seed(8)).cuda()
+    with torch.no_grad():
+        io0, ps0 = m(x)
+        io0, ps0 = io0.clone(), [p.clone() for p in ps0]
+        mh = m.half()
+        io1, ps1 = mh(x.half())
+    assert io1.dtype == torch.float32
+    for a, b in zip(ps0, ps1):
+        assert float((a - b).abs().max()) <= 2e-2 * float(a.abs().max())
+    mh.train()
+    with pytest.raises(RuntimeError):
+        mh(x)                                               # the fused training step needs fp32 master parameters
