@@ -130,6 +130,7 @@ struct ConvParams {
   int res_cs;         // channel stride of the residual buffer
   int has_act, has_res, upsample2x, out_f32_nchw;
   int tma_store;      // bf16 stride-1 non-upsampled output: tiles leave (and residuals arrive) through TMA, 64-filter groups
+  int arow_bo;        // A-row experiments: 1 = put the line shift into the descriptor's base-offset field as well
   int dbg;            // measurement knob RYOLO_CONV_DEBUG (scratch/conv_exp.py): timing experiments only, 0 in production
   float slope;
   const float* bias;               // [cout_pad]
@@ -290,7 +291,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               }
               // tap dxi = rows [dxi, dxi + 128) of the A-row box: start shifted by dxi 128-byte lines, and since that start
               // is not aligned to the 1024-byte swizzle pattern any more, the descriptor's base offset says so
-              const uint64_t adesc = make_smem_desc(sa + dxi * 128) | ((uint64_t)dxi << 49);
+              const uint64_t adesc = make_smem_desc(sa + dxi * 128) | (p.arow_bo ? ((uint64_t)dxi << 49) : 0ull);
               const uint64_t bdesc = make_smem_desc(smem_base + S::kBRingOffset + bs * S::kBBytes);
 #pragma unroll
               for (int k = 0; k < BK / 16; k++) {
@@ -792,6 +793,12 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
     arow_env = e ? atoi(e) : 0;   // default off until the shifted-descriptor form is validated on hardware (profiles/)
   }
   const bool arow = arow_env != 0 && g.taps > 1 && dbg == 0;
+  static int arow_bo = -1;
+  if (arow_bo < 0) {
+    const char* e = getenv("RYOLO_CONV_AROW_BO");
+    arow_bo = e ? atoi(e) : 1;
+  }
+  p.arow_bo = arow_bo;
   CUtensorMap ma, mb;
   const int a_inner = d->cin_stride < g.cin_pad ? d->cin_stride : g.cin_pad;
   int st = encode_map_2d(&ma, x, (uint64_t)a_inner, (uint64_t)p.np, (uint64_t)d->cin_stride * 2, BK, arow ? BM + 8 : BM);
