@@ -339,7 +339,7 @@ def timed_steps(ctx, step, K, W, pre_step=None):
     ctx.barrier()
     if ctx.rank == 0:
         sampler.start()
-    l0 = ctx.lib.ryolo_launch_count()
+    l0 = ctx.lib.ryolo_launch_count() + (ctx.replayed() if getattr(ctx, "replayed", None) else 0)
     for i in range(K):
         if pre_step:
             pre_step(i)          # e.g. L2 flush: outside the per-step events
@@ -347,7 +347,7 @@ def timed_steps(ctx, step, K, W, pre_step=None):
         step(i)
         ev[i][1].record()
     ctx.barrier()
-    launches = ctx.lib.ryolo_launch_count() - l0
+    launches = ctx.lib.ryolo_launch_count() + (ctx.replayed() if getattr(ctx, "replayed", None) else 0) - l0
     clocks = sampler.stop() if ctx.rank == 0 else None
     per_step = [s.elapsed_time(e) for s, e in ev]
     t = torch.tensor([sum(per_step)], dtype=torch.float64, device=ctx.dev)
@@ -588,7 +588,10 @@ def wl_train(ctx, K, W, full=True, precision="bf16"):
             net.use_cuda_graph = False
             net._tplan = None
             torch.cuda.synchronize()
+    # kernels executed through CUDA-graph replays are counted from the capture (the library's launch counter only sees eager calls)
+    ctx.replayed = lambda: (net._tplan.replayed_kernels if getattr(net, "_tplan", None) is not None else 0)
     ms, per_step, launches, clocks = timed_steps(ctx, step, K, W)
+    ctx.replayed = None
     e2e_ms = timed_e2e(ctx, step_e2e, K)
     # one more step with stage timers on EVERY rank (it contains the collective)
     tm = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -672,7 +675,9 @@ def wl_detect(ctx, K, W, full=True):
         res = run(xd)
         counts_h.copy_(res["num_keep"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+    ctx.replayed = lambda: model.replayed_kernels
     ms, per_step, launches, clocks = timed_steps(ctx, step, K, W)
+    ctx.replayed = None
     e2e_ms = timed_e2e(ctx, step_e2e, K)
     out = None
     if ctx.rank == 0:

@@ -11,8 +11,10 @@
 // plus the small layout kernels of the training graph (zero insertion for stride-2 adjoints, NCHW fp32 -> padded
 // NHWC bf16 for the head gradients, im2col of the 3-channel image so that the first layer runs on the same GEMMs).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 
 namespace ryolo {
 
@@ -84,31 +86,29 @@ __global__ void __launch_bounds__(BNT) bn_stats_kernel(const __nv_bfloat16* __re
   const RowSpan rs = row_span(g);
   const int nrows = g.batch * g.h;
   const int row_begin = blockIdx.x * rows_per_block, row_end = min(nrows, row_begin + rows_per_block);
-  float s1[8], s2[8];
+  // packed fp32x2 accumulators: 16 instructions per 16-byte load instead of 24
+  uint64_t p1[4], p2[4];
 #pragma unroll
-  for (int e = 0; e < 8; e++) s1[e] = s2[e] = 0.f;
-  constexpr int U = 4;   // independent 16-byte loads in flight per thread (a dependent load->add chain reaches ~55 % of HBM)
+  for (int e = 0; e < 4; e++) p1[e] = p2[e] = 0ull;
   for (int row = row_begin; row < row_end; row++) {
     const int b = row / g.h, y = row - b * g.h;
     const __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, zcs) + rs.cg * 8;
-    for (int x0 = rs.px0; x0 < g.w; x0 += U * rs.pstep) {
-      uint4 v[U];
+    for (int x = rs.px0; x < g.w; x += rs.pstep) {
+      const uint4 v = *reinterpret_cast<const uint4*>(zr + (size_t)x * zcs);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int x = x0 + u * rs.pstep;
-        v[u] = x < g.w ? __ldg(reinterpret_cast<const uint4*>(zr + (size_t)x * zcs)) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        float f[8];
-        unpack8(v[u], f);
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          s1[e] += f[e];
-          s2[e] = fmaf(f[e], f[e], s2[e]);
-        }
+      for (int e = 0; e < 4; e++) {
+        const uint64_t f2 = bf2_to_f2(w[e]);
+        p1[e] = f2add(p1[e], f2);
+        p2[e] = f2fma(f2, f2, p2[e]);
       }
     }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    f2unpack(p1[e], s1[2 * e], s1[2 * e + 1]);
+    f2unpack(p2[e], s2[2 * e], s2[2 * e + 1]);
   }
 #pragma unroll
   for (int e = 0; e < 8; e++) {
@@ -180,7 +180,7 @@ __device__ __forceinline__ void load_dy(const __nv_bfloat16* __restrict__ dy, in
   }
 }
 
-__global__ void __launch_bounds__(BNT) bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, int up,
+__global__ void __launch_bounds__(BNT, 3) bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, int up,
                                                                 const __nv_bfloat16* __restrict__ z, int zcs, Geo g,
                                                                 const float* __restrict__ scale,
                                                                 const float* __restrict__ shift,
@@ -200,54 +200,47 @@ __global__ void __launch_bounds__(BNT) bn_act_bwd_reduce_kernel(const __nv_bfloa
   load8(invstd, rs.cg, is);
   const int nrows = g.batch * g.h;
   const int row_begin = blockIdx.x * rows_per_block, row_end = min(nrows, row_begin + rows_per_block);
-  float a1[8], a2[8], asl = 0.f;
+  float asl = 0.f;
+  uint64_t sc2[4], sh2[4], nmu2[4], is2[4], q1[4], q2[4];
 #pragma unroll
-  for (int e = 0; e < 8; e++) a1[e] = a2[e] = 0.f;
-  constexpr int U = 2;   // pixels per iteration: both tensors' loads of both pixels are issued before any arithmetic
+  for (int e = 0; e < 4; e++) {
+    sc2[e] = f2pack(sc[2 * e], sc[2 * e + 1]);
+    sh2[e] = f2pack(sh[2 * e], sh[2 * e + 1]);
+    nmu2[e] = f2pack(-mu[2 * e], -mu[2 * e + 1]);
+    is2[e] = f2pack(is[2 * e], is[2 * e + 1]);
+    q1[e] = q2[e] = 0ull;
+  }
   for (int row = row_begin; row < row_end; row++) {
     const int b = row / g.h, y = row - b * g.h;
     const __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, zcs) + rs.cg * 8;
-    const __nv_bfloat16* dr = dy + pad_off(b, y, 0, g.h, g.w, dcs) + rs.cg * 8;
-    for (int x0 = rs.px0; x0 < g.w; x0 += U * rs.pstep) {
-      uint4 zv[U], dv[U];
-      float d[U][8];
+    for (int x = rs.px0; x < g.w; x += rs.pstep) {
+      const uint4 zv = *reinterpret_cast<const uint4*>(zr + (size_t)x * zcs);
+      float d[8];
+      load_dy(dy, dcs, g, b, y, x, rs.cg, up, d);
+      const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
 #pragma unroll
-      for (int q = 0; q < U; q++) {
-        const int x = x0 + q * rs.pstep;
-        const bool live = x < g.w;
-        zv[q] = live ? __ldg(reinterpret_cast<const uint4*>(zr + (size_t)x * zcs)) : make_uint4(0, 0, 0, 0);
-        if (!up) dv[q] = live ? __ldg(reinterpret_cast<const uint4*>(dr + (size_t)x * dcs)) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int q = 0; q < U; q++) {
-        const int x = x0 + q * rs.pstep;
-        if (!up) {
-          unpack8(dv[q], d[q]);
-        } else if (x < g.w) {
-          load_dy(dy, dcs, g, b, y, x, rs.cg, up, d[q]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; e++) d[q][e] = 0.f;
+      for (int e = 0; e < 4; e++) {
+        // two channels per step in packed fp32x2: u = z*scale + shift, zhat = (z - mean) * invstd
+        const uint64_t f2 = bf2_to_f2(zw[e]);
+        float u0, u1;
+        f2unpack(f2fma(f2, sc2[e], sh2[e]), u0, u1);
+        float du0 = d[2 * e], du1 = d[2 * e + 1];
+        if (has_act) {
+          if (!(u0 > 0.f)) { asl = fmaf(du0, u0, asl); du0 *= slope; }
+          if (!(u1 > 0.f)) { asl = fmaf(du1, u1, asl); du1 *= slope; }
         }
-      }
-#pragma unroll
-      for (int q = 0; q < U; q++) {
-        float f[8];
-        unpack8(zv[q], f);
-#pragma unroll
-        for (int e = 0; e < 8; e++) {       // dead pixels carry dy = 0: they add nothing to any sum
-          const float u = fmaf(f[e], sc[e], sh[e]);
-          float du = d[q][e];
-          if (has_act && !(u > 0.f)) {
-            asl = fmaf(d[q][e], u, asl);
-            du *= slope;
-          }
-          const float zh = (f[e] - mu[e]) * is[e];
-          a1[e] += du;
-          a2[e] = fmaf(du, zh, a2[e]);
-        }
+        const uint64_t du2 = f2pack(du0, du1);
+        const uint64_t zh2 = f2mul(f2add(f2, nmu2[e]), is2[e]);
+        q1[e] = f2add(q1[e], du2);
+        q2[e] = f2fma(du2, zh2, q2[e]);
       }
     }
+  }
+  float a1[8], a2[8];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    f2unpack(q1[e], a1[2 * e], a1[2 * e + 1]);
+    f2unpack(q2[e], a2[2 * e], a2[2 * e + 1]);
   }
 #pragma unroll
   for (int e = 0; e < 8; e++) {
@@ -283,6 +276,16 @@ __global__ void __launch_bounds__(BNT) bn_act_bwd_apply_kernel(const __nv_bfloat
   for (int e = 0; e < 8; e++) {
     m1[e] *= inv_n;
     m2[e] *= inv_n;
+  }
+  uint64_t sc2[4], sh2[4], nmu2[4], is2[4], nm12[4], nm22[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    sc2[e] = f2pack(sc[2 * e], sc[2 * e + 1]);
+    sh2[e] = f2pack(sh[2 * e], sh[2 * e + 1]);
+    nmu2[e] = f2pack(-mu[2 * e], -mu[2 * e + 1]);
+    is2[e] = f2pack(is[2 * e], is[2 * e + 1]);
+    nm12[e] = f2pack(-m1[2 * e], -m1[2 * e + 1]);
+    nm22[e] = f2pack(-m2[2 * e], -m2[2 * e + 1]);
   }
   const int nrows = g.batch * g.h;
   const int row_begin = blockIdx.x * rows_per_block, row_end = min(nrows, row_begin + rows_per_block);
@@ -322,14 +325,27 @@ __global__ void __launch_bounds__(BNT) bn_act_bwd_apply_kernel(const __nv_bfloat
           }
           *reinterpret_cast<uint4*>(gr + (size_t)x * gcs) = pack8(o);
         }
-        float f[8], out[8];
-        unpack8(zv[q], f);
+        float out[8];
+        const uint32_t zw[4] = {zv[q].x, zv[q].y, zv[q].z, zv[q].w};
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-          const float u = fmaf(f[e], sc[e], sh[e]);
-          float du = d[q][e];
-          if (has_act && !(u > 0.f)) du *= slope;
-          out[e] = has_bn ? sc[e] * (du - m1[e] - (f[e] - mu[e]) * is[e] * m2[e]) : du;
+        for (int e = 0; e < 4; e++) {      // two channels per step, packed fp32x2
+          const uint64_t f2 = bf2_to_f2(zw[e]);
+          float u0, u1;
+          f2unpack(f2fma(f2, sc2[e], sh2[e]), u0, u1);
+          float du0 = d[q][2 * e], du1 = d[q][2 * e + 1];
+          if (has_act) {
+            if (!(u0 > 0.f)) du0 *= slope;
+            if (!(u1 > 0.f)) du1 *= slope;
+          }
+          if (has_bn) {
+            // sc * (du - m1 - zhat * m2),  zhat = (z - mean) * invstd
+            const uint64_t zh2 = f2mul(f2add(f2, nmu2[e]), is2[e]);
+            const uint64_t t2 = f2fma(zh2, nm22[e], f2add(f2pack(du0, du1), nm12[e]));
+            f2unpack(f2mul(sc2[e], t2), out[2 * e], out[2 * e + 1]);
+          } else {
+            out[2 * e] = du0;
+            out[2 * e + 1] = du1;
+          }
         }
         *reinterpret_cast<uint4*>(zr + (size_t)x * zcs) = pack8(out);
       }
@@ -523,7 +539,12 @@ static inline size_t n_items(const Geo& g) { return (size_t)g.batch * g.h * g.w 
 static inline int rows_per_block(const Geo& g) {
   const int cgs = g.c >> 3;
   long long per_row = (long long)g.w * cgs;
-  int r = (int)((16384 + per_row - 1) / per_row);
+  static int target = -1;
+  if (target < 0) {
+    const char* e = getenv("RYOLO_BN_ITEMS");     // measurement knob: 16-byte items per CTA
+    target = e ? atoi(e) : 16384;
+  }
+  int r = (int)((target + per_row - 1) / per_row);
   const int nrows = g.batch * g.h;
   const int max_r = (nrows + 591) / 592;
   if (r > max_r) r = max_r;

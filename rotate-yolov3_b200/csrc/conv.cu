@@ -144,10 +144,11 @@ struct ConvParams {
 // AROW ("one A load per kernel row").  The taps of one kernel row (dx = -1, 0, +1) read the SAME pixels shifted by one
 // row of the flat pixel index, i.e. by one 128-byte line of the swizzled tile.  With AROW the producer loads ONE box of
 // BM + 8 rows per (kernel row, k-chunk) and the MMA issuer addresses tap dx through a descriptor whose start is shifted
-// by dx lines (matrix base offset = dx: the start is no longer aligned to the 1024-byte swizzle pattern) -- a third of
-// the A traffic.  Measured motivation: every 3x3 layer moved ~36-54 B/clk/SM from L2, at or beyond the ~42 B/clk/SM the
-// LTS can deliver to 148 SMs (B300_MICROARCH.md: ~6300 B/cyc chip-wide): the kernel was L2-throughput bound.  A and B
-// then live in separate rings (A stage = 18 KB every 3 taps, B stage = BN x 128 B every tap).
+// by dx lines -- a third of the A traffic.  Motivation (ncu, profiles/r02_prof_thin_summary.csv): on the thin 304^2
+// layers the tensor pipe is 21 % active and 43 % of all stall samples are epilogue warps waiting for the accumulator,
+// i.e. the MMA warp starves on operands: the per-tap A boxes are DISTINCT data for every CTA (unlike the weights, which
+// all CTAs request at the same time and L2 serves once), ~27 B/clk/SM of distinct L2 reads.  A and B live in separate
+// rings (A stage = 18 KB every 3 taps, B stage = BN x 128 B every tap).
 //
 // BRES ("resident weights", thin layers).  With cout <= 64 there is ONE n-tile, so every tile of the CTA multiplies by the
 // same <= 72 KB of packed weights; after AROW the per-tile weight re-load (9 x 8 KB) was the larger half of the L2 traffic
@@ -289,8 +290,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 mbar_wait(bfull_bar(bs), bph);
                 tc_fence_after();
               }
-              // tap dxi = rows [dxi, dxi + 128) of the A-row box: start shifted by dxi 128-byte lines, and since that start
-              // is not aligned to the 1024-byte swizzle pattern any more, the descriptor's base offset says so
+              // tap dxi = rows [dxi, dxi + 128) of the A-row box: the descriptor start is shifted by dxi 128-byte lines.
+              // Measured on B200: the 128B swizzle is a function of the shared-memory ADDRESS bits (what TMA wrote at line
+              // r is found at line r whatever the start), so the descriptor's base-offset field must stay 0 -- with
+              // base offset = dxi every multi-tap layer is wrong (gpurun_out/r02_pytest_arow.log vs r02_pytest_arow_bo0.log)
               const uint64_t adesc = make_smem_desc(sa + dxi * 128) | (p.arow_bo ? ((uint64_t)dxi << 49) : 0ull);
               const uint64_t bdesc = make_smem_desc(smem_base + S::kBRingOffset + bs * S::kBBytes);
 #pragma unroll
@@ -790,13 +793,13 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   static int arow_env = -1;
   if (arow_env < 0) {
     const char* e = getenv("RYOLO_CONV_AROW");
-    arow_env = e ? atoi(e) : 0;   // default off until the shifted-descriptor form is validated on hardware (profiles/)
+    arow_env = e ? atoi(e) : 2;   // validated on B200: tests/test_conv_gpu.py etc. pass with 1 and 2 (gpurun_out/r02_pytest_arow2_bo0.log)
   }
   const bool arow = arow_env != 0 && g.taps > 1 && dbg == 0;
   static int arow_bo = -1;
   if (arow_bo < 0) {
     const char* e = getenv("RYOLO_CONV_AROW_BO");
-    arow_bo = e ? atoi(e) : 1;
+    arow_bo = e ? atoi(e) : 0;    // 0 is the correct form (see the kernel comment); 1 kept as the record of the experiment
   }
   p.arow_bo = arow_bo;
   CUtensorMap ma, mb;

@@ -195,6 +195,7 @@ class Darknet(nn.Module):
         # buffers that the next forward overwrites (standard CUDA-graph semantics), hence not the default.
         self.use_cuda_graph = False
         self._graph = None
+        self.replayed_kernels = 0
 
     # ------------------------------------------------------------------------------------------------------
     def fuse(self):
@@ -454,11 +455,14 @@ class Darknet(nn.Module):
                     self._run_eval(self._x_static, b, h, w)          # warm-up (attribute calls, lazy inits) outside capture
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
+                    c0 = _lib.lib.ryolo_launch_count()
                     with torch.cuda.graph(g):
                         self._graph_out = self._run_eval(self._x_static, b, h, w)
                     self._graph = g
+                    self._graph_kernels = int(_lib.lib.ryolo_launch_count() - c0)
                 self._x_static.copy_(x)
                 self._graph.replay()
+                self.replayed_kernels += self._graph_kernels     # this library's kernels executed by the replay
                 return self._graph_out
             return self._run_eval(x, b, h, w)
 

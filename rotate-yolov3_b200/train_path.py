@@ -201,6 +201,7 @@ class TrainPlan:
         self.gen = 0                 # forward generation: backward must see the activations of ITS forward
         self.consumed = True
         self.graphs = None           # CUDA graphs of forward / backward segments (model.use_cuda_graph)
+        self.replayed_kernels = 0    # kernels of this library executed through CUDA-graph replays (bench.py gpu_launches)
         self.time_comm = False       # bench.py: record events around the wait for the all-reduces (exposed time)
         self._comm_ev = None
 
@@ -437,14 +438,17 @@ class TrainPlan:
             eager = self._forward_body(self.x_static)         # this call's forward, eagerly (also the capture warm-up)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
+            c0 = _lib.lib.ryolo_launch_count()
             with torch.cuda.graph(g):
                 outs = self._forward_body(self.x_static)      # captured, not executed
             self.graphs["pool"] = g.pool()
             self.graphs["fwd"] = (g, outs)
+            self.graphs["fwd_kernels"] = int(_lib.lib.ryolo_launch_count() - c0)   # this library's kernels in the graph
             return eager
         g, outs = self.graphs["fwd"]
         self.x_static.copy_(x)
         g.replay()
+        self.replayed_kernels += self.graphs["fwd_kernels"]
         return outs
 
     # ------------------------------------------------------------------------------------------------------
@@ -513,18 +517,22 @@ class TrainPlan:
             inv = self.buckets.finish() if self.buckets else 1.0
             out_flat = self.garena * inv
             torch.cuda.synchronize(self.device)
-            gs = []
+            gs, gk = [], []
             for si in range(len(self.segments)):
                 g = torch.cuda.CUDAGraph()
+                c0 = _lib.lib.ryolo_launch_count()
                 with torch.cuda.graph(g, pool=self.graphs["pool"]):
                     self._backward_segment(si)
                 gs.append(g)
+                gk.append(int(_lib.lib.ryolo_launch_count() - c0))
+            self.graphs["bwd_kernels"] = gk
             self.graphs["bwd"] = gs
             # the capture passes did not execute; the eager pass above produced this step's gradients
         else:
             for si, seg in enumerate(self.segments):
                 if use_graph:
                     self.graphs["bwd"][si].replay()
+                    self.replayed_kernels += self.graphs["bwd_kernels"][si]
                 else:
                     self._backward_segment(si)
                 if self.buckets:
