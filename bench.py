@@ -785,6 +785,8 @@ def main():
     ctx.args, ctx.rank, ctx.world, ctx.local_rank = args, rank, world, local_rank
     ctx.dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the gradient all-reduce runs NEXT to the backward GEMMs, which leave it 8 SMs (parallel.DistributedDataParallel)
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")
         dist.init_process_group("nccl", device_id=ctx.dev)
     ctx.pk, ctx.pkg, ctx.lib = peaks(), pkg, pkg._lib.lib
 

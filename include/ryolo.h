@@ -43,6 +43,10 @@ const char* ryolo_last_error(void);
 /* Number of this library's kernel launches issued by the calling process so far
  * (bench.py's `gpu_launches` evidence). */
 uint64_t ryolo_launch_count(void);
+/* Keep n SMs free of this library's persistent GEMM kernels (conv fwd / dgrad / wgrad grids = SM count - n) from now on:
+ * a data-parallel training step reserves a few SMs during backward so that the concurrent NCCL all-reduce kernels are
+ * resident next to them instead of forcing a second wave (process-wide setting, 0 <= n <= 64; 0 = use every SM). */
+int ryolo_set_reserved_sms(int n);
 
 /* ------------------------------------------------------------------------------------------ *
  * Rotated NMS  (reference: r_nms / nms_cuda, rotate_polygon_nms_kernel.cu:323-384)

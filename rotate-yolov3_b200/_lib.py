@@ -51,6 +51,7 @@ SIGNATURES = {
     "ryolo_abi_version": (_i, []),
     "ryolo_last_error": (ctypes.c_char_p, []),
     "ryolo_launch_count": (ctypes.c_uint64, []),
+    "ryolo_set_reserved_sms": (_i, [_i]),
     "ryolo_rnms_workspace_bytes": (_sz, [_i]),
     "ryolo_rnms": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "ryolo_rnms_full_mask": (_i, [_vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),

@@ -66,6 +66,16 @@ inline int device_sm_count() {
   }
   return n;
 }
+// SMs a persistent GEMM kernel may occupy: all of them, minus a reserve that a data-parallel training step keeps free for
+// the NCCL all-reduce CTAs running concurrently on a side stream (ryolo_set_reserved_sms).  A persistent kernel with a
+// static tile schedule that finds some SMs busy runs its surplus CTAs as a second wave -- twice the time; with a few SMs
+// reserved both kernels are resident at once.
+extern std::atomic<int> g_reserved_sms;
+inline int gemm_sm_count() {
+  const int n = device_sm_count(), r = g_reserved_sms.load(std::memory_order_relaxed);
+  return n - r > 8 ? n - r : n;
+}
+
 #define RYOLO_SMEM_OPT_IN(kernel, bytes)                                                                      \
   do {                                                                                                        \
     static std::atomic<uint64_t> _mask{0};                                                                    \

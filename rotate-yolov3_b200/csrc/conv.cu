@@ -674,7 +674,7 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
   using S = ConvSmem<BN, NBUF, AROW, BRES>;
   static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
   RYOLO_SMEM_OPT_IN((conv_igemm_kernel<BN, NBUF, AROW, BRES>), S::kTotal);
-  const int num_sms = device_sm_count();
+  const int num_sms = gemm_sm_count();
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   conv_igemm_kernel<BN, NBUF, AROW, BRES><<<grid, CONV_THREADS, S::kTotal, stream>>>(ma, mb, mo, mr, p);

@@ -7,6 +7,7 @@
 namespace ryolo {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_reserved_sms{0};
 
 char* err_buf() {
   static thread_local char buf[512] = {0};
@@ -180,6 +181,12 @@ using namespace ryolo;
 extern "C" int ryolo_abi_version(void) { return 1; }
 extern "C" const char* ryolo_last_error(void) { return err_buf(); }
 extern "C" uint64_t ryolo_launch_count(void) { return g_launches.load(); }
+
+extern "C" int ryolo_set_reserved_sms(int n) {
+  if (n < 0 || n > 64) return RYOLO_E_ARG;
+  ryolo::g_reserved_sms.store(n, std::memory_order_relaxed);
+  return RYOLO_OK;
+}
 
 extern "C" size_t ryolo_nms_filter_workspace_bytes(int p) {
   const int nblocks = (p > 0 ? p : 0) / FT + 1;

@@ -208,7 +208,7 @@ extern "C" int ryolo_conv_wgrad(const void* dz, int dz_cstride, int cout_pad, co
   p.m_tiles = (cout_pad + WG_BM - 1) / WG_BM;
   p.n_tiles = (cin_pad + bn - 1) / bn;
   p.ksteps_total = (p.np + WG_BK - 1) / WG_BK;
-  const int num_sms = device_sm_count();
+  const int num_sms = gemm_sm_count();
   // taps per CTA: the kernel row (3 or 2 taps) when the accumulators fit TMEM and the layer is thin enough to be
   // operand-stream bound; RYOLO_WGRAD_TG=1 forces one tap per CTA (measurement knob)
   static int force_tg = -1;

@@ -119,10 +119,11 @@ class DistributedDataParallel(torch.nn.Module):
     finished gradient buckets to GradBuckets, so the NCCL all-reduce of bucket k overlaps the backward kernels of the
     blocks before it; the gradients autograd receives are already averaged over the ranks."""
 
-    def __init__(self, module, bucket_mb=32, process_group=None):
+    def __init__(self, module, bucket_mb=32, process_group=None, reserved_sms=8):
         super().__init__()
         self.module = module
-        module._ddp = {"bucket_bytes": int(bucket_mb) << 20, "group": process_group}
+        # reserved_sms: SMs the backward GEMMs leave to the concurrent NCCL kernels (pair it with NCCL_MAX_NCHANNELS <= 8)
+        module._ddp = {"bucket_bytes": int(bucket_mb) << 20, "group": process_group, "reserved_sms": int(reserved_sms)}
         module._tplan = None          # the plan builds its buckets at construction
         module._pplan = None
 

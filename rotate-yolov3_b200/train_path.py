@@ -506,6 +506,19 @@ class TrainPlan:
 
     def backward(self, grads):
         m = self.model
+        overlap = self.buckets is not None and self.buckets.world > 1
+        if overlap:
+            # leave a few SMs to the NCCL all-reduce kernels that run next to the backward GEMMs (persistent kernels with a
+            # static tile schedule would otherwise run a second wave on the SMs NCCL occupies)
+            _lib.lib.ryolo_set_reserved_sms(int(getattr(m, "_ddp", {}).get("reserved_sms", 8)))
+        try:
+            return self._backward(grads)
+        finally:
+            if overlap:
+                _lib.lib.ryolo_set_reserved_sms(0)
+
+    def _backward(self, grads):
+        m = self.model
         self._head_grads(grads)
         use_graph = getattr(m, "use_cuda_graph", False) and self.graphs is not None and "fwd" in self.graphs
         if use_graph and "bwd" not in self.graphs:
