@@ -353,6 +353,7 @@ def timed_steps(ctx, step, K, W, pre_step=None):
     t = torch.tensor([sum(per_step)], dtype=torch.float64, device=ctx.dev)
     if ctx.world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ctx.last_per_step = [round(v, 3) for v in per_step]       # rank 0's own steps (the reported time is the max over ranks)
     return float(t.item()) / K, per_step, int(launches), clocks
 
 
@@ -615,6 +616,8 @@ def wl_train(ctx, K, W, full=True, precision="bf16"):
         notes.update({"collective": "bucketed NCCL all-reduce of 62.4M fp32 gradients (32 MB buckets in backward order), "
                                   "overlapped with backward" if world > 1 else "none (1 rank)",
                     "cuda_graph": bool(net.use_cuda_graph) if graph_note is None else graph_note,
+                    "rank0_per_step_ms": getattr(ctx, "last_per_step", None),
+                    "reserved_sms": (net._ddp or {}).get("reserved_sms") if getattr(net, "_ddp", None) else 0,
                     "arithmetic": "bf16 operands/activations, fp32 accumulate and parameter gradients" if precision == "bf16"
                     else "fp32-grade: 3 bf16 planes per operand, 6 exact-product terms, fp32 round-to-nearest sums, fp64 "
                          "reductions (parity_path.py); matches the reference's fp32 modules to 1e-4",
@@ -785,8 +788,9 @@ def main():
     ctx.args, ctx.rank, ctx.world, ctx.local_rank = args, rank, world, local_rank
     ctx.dev = torch.device("cuda", local_rank)
     if world > 1:
-        # the gradient all-reduce runs NEXT to the backward GEMMs, which leave it 8 SMs (parallel.DistributedDataParallel)
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")
+        # the gradient all-reduce runs NEXT to the backward GEMMs: cap the SMs NCCL may take (measured at 2 GPUs: 16 channels
+        # 40.4 ms/step, 8 channels 41.2; profiles/r02_n2_experiments.txt)
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "16")
         dist.init_process_group("nccl", device_id=ctx.dev)
     ctx.pk, ctx.pkg, ctx.lib = peaks(), pkg, pkg._lib.lib
 

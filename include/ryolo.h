@@ -298,9 +298,16 @@ int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, int w, int 
                      const float* scale, const float* shift, float slope, int has_act,
                      const void* residual, int res_cstride, void* y, int y_cstride, int upsample2x,
                      const float* slope_dev, void* stream);
+/* Same, and additionally writes y in the space-to-depth layout of ryolo_space_to_depth into xs (the operand of a
+ * following 3x3/stride-2 block): the separate s2d pass over y disappears.  h, w even. */
+int ryolo_bn_act_fwd_s2d(const void* z, int z_cstride, int batch, int h, int w, int c,
+                         const float* scale, const float* shift, float slope, int has_act,
+                         const void* residual, int res_cstride, void* y, int y_cstride,
+                         const float* slope_dev, void* xs, int xs_cstride, void* stream);
 /* slope_dev (both directions, optional): device scalar holding the PReLU slope (nn.PReLU.weight);
  * when non-null it replaces `slope`, so a training step never copies the parameter to the host.
- * Backward of the same block.  dy: gradient of y (at 2h x 2w when upsample2x).  z_dz: in = z, out =
+ * Backward of the same block.  dy: gradient of y (at 2h x 2w when upsample2x == 1; upsample2x == 2: dy is read in the
+ * space-to-depth layout [B, h/2+2, w/2+2, >=4c] a consuming 3x3/stride-2 block's dgrad wrote, no depth_to_space pass).  z_dz: in = z, out =
  * dz (gradient of the raw conv output, written in place).  sums (fp32 [2c+1], zeroed inside):
  * [0..c) = d(beta), [c..2c) = d(gamma), [2c] = d(slope).  gres (optional): gradient buffer of the
  * shortcut source, receives (+)= dy. */

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(BNT) bn_act_fwd_kernel(const __nv_bfloat16* __
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          float slope, int has_act, const __nv_bfloat16* __restrict__ res,
                                                          int rcs, __nv_bfloat16* __restrict__ y, int ycs, int up,
-                                                         int rows_per_block, const float* __restrict__ slope_dev) {
+                                                         int rows_per_block, const float* __restrict__ slope_dev,
+                                                         __nv_bfloat16* __restrict__ xs, int xcs) {
   if (slope_dev) slope = __ldg(slope_dev);
   const RowSpan rs = row_span(g);
   float sc[8], sh[8];
@@ -149,6 +150,9 @@ __global__ void __launch_bounds__(BNT) bn_act_fwd_kernel(const __nv_bfloat16* __
       const uint4 o = pack8(f);
       if (!up) {
         *reinterpret_cast<uint4*>(y + pad_off(b, yy, x, g.h, g.w, ycs) + rs.cg * 8) = o;
+        // second copy in the space-to-depth layout of a following 3x3/stride-2 block (saves its s2d pass over y)
+        if (xs) *reinterpret_cast<uint4*>(xs + pad_off(b, yy >> 1, x >> 1, g.h >> 1, g.w >> 1, xcs) +
+                                          ((yy & 1) * 2 + (x & 1)) * g.c + rs.cg * 8) = o;
       } else {
 #pragma unroll
         for (int ry = 0; ry < 2; ry++)
@@ -160,10 +164,18 @@ __global__ void __launch_bounds__(BNT) bn_act_fwd_kernel(const __nv_bfloat16* __
   }
 }
 
-// dy for one 8-channel group; possibly at 2x resolution (sum of the 2x2 block = adjoint of nearest upsample)
+// dy for one 8-channel group; up = 1: at 2x resolution (sum of the 2x2 block = adjoint of nearest upsample); up = 2: dy
+// lives in the space-to-depth layout of the consuming 3x3/stride-2 block (its dgrad output, read in place instead of
+// being scattered back by a depth_to_space pass)
+__device__ __forceinline__ const __nv_bfloat16* dy_s2d_ptr(const __nv_bfloat16* __restrict__ dy, int dcs, const Geo& g, int b,
+                                                           int y, int x, int cg) {
+  return dy + pad_off(b, y >> 1, x >> 1, g.h >> 1, g.w >> 1, dcs) + ((y & 1) * 2 + (x & 1)) * g.c + cg * 8;
+}
 __device__ __forceinline__ void load_dy(const __nv_bfloat16* __restrict__ dy, int dcs, const Geo& g, int b, int y, int x,
                                         int cg, int up, float* d) {
-  if (!up) {
+  if (up == 2) {
+    unpack8(*reinterpret_cast<const uint4*>(dy_s2d_ptr(dy, dcs, g, b, y, x, cg)), d);
+  } else if (!up) {
     unpack8(*reinterpret_cast<const uint4*>(dy + pad_off(b, y, x, g.h, g.w, dcs) + cg * 8), d);
   } else {
 #pragma unroll
@@ -304,6 +316,7 @@ __global__ void __launch_bounds__(BNT) bn_act_bwd_apply_kernel(const __nv_bfloat
         if (x < g.w) {
           zv[q] = *reinterpret_cast<const uint4*>(zr + (size_t)x * zcs);
           if (!up) dv[q] = __ldg(reinterpret_cast<const uint4*>(dr + (size_t)x * dcs));
+          else if (up == 2) dv[q] = __ldg(reinterpret_cast<const uint4*>(dy_s2d_ptr(dy, dcs, g, b, y, x, rs.cg)));
           if (gr && gres_acc) gv[q] = *reinterpret_cast<const uint4*>(gr + (size_t)x * gcs);
         }
       }
@@ -311,7 +324,7 @@ __global__ void __launch_bounds__(BNT) bn_act_bwd_apply_kernel(const __nv_bfloat
       for (int q = 0; q < U; q++) {
         const int x = x0 + q * rs.pstep;
         if (x >= g.w) continue;
-        if (!up) unpack8(dv[q], d[q]);
+        if (up != 1) unpack8(dv[q], d[q]);
         else load_dy(dy, dcs, g, b, y, x, rs.cg, up, d[q]);
         if (gr) {  // shortcut branch: d(residual) (+)= dy   (never combined with upsample)
           float o[8];
@@ -574,22 +587,39 @@ extern "C" int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, in
   return RYOLO_OK;
 }
 
-extern "C" int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, int w, int c, const float* scale,
-                                const float* shift, float slope, int has_act, const void* residual, int res_cstride,
-                                void* y, int y_cstride, int upsample2x, const float* slope_dev, void* stream_) {
+static int bn_act_fwd_impl(const void* z, int z_cstride, int batch, int h, int w, int c, const float* scale,
+                           const float* shift, float slope, int has_act, const void* residual, int res_cstride, void* y,
+                           int y_cstride, int upsample2x, const float* slope_dev, void* xs, int xs_cstride, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(z && scale && shift && y);
   GEO_CHECK();
   RYOLO_ARG_CHECK(!(residual && upsample2x));
+  RYOLO_ARG_CHECK(!xs || (!upsample2x && h % 2 == 0 && w % 2 == 0 && xs_cstride >= 4 * c && xs_cstride % 8 == 0));
   GEO_CHECK_P2();
   const Geo g = mk_geo(batch, h, w, c);
   const int rpb = rows_per_block(g);
   bn_act_fwd_kernel<<<(unsigned)((batch * h + rpb - 1) / rpb), BNT, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(z), z_cstride, g, scale, shift, slope, has_act,
       static_cast<const __nv_bfloat16*>(residual), res_cstride, static_cast<__nv_bfloat16*>(y), y_cstride, upsample2x, rpb,
-      slope_dev);
+      slope_dev, static_cast<__nv_bfloat16*>(xs), xs_cstride);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
+}
+
+extern "C" int ryolo_bn_act_fwd(const void* z, int z_cstride, int batch, int h, int w, int c, const float* scale,
+                                const float* shift, float slope, int has_act, const void* residual, int res_cstride,
+                                void* y, int y_cstride, int upsample2x, const float* slope_dev, void* stream_) {
+  return bn_act_fwd_impl(z, z_cstride, batch, h, w, c, scale, shift, slope, has_act, residual, res_cstride, y, y_cstride,
+                         upsample2x, slope_dev, nullptr, 0, stream_);
+}
+
+extern "C" int ryolo_bn_act_fwd_s2d(const void* z, int z_cstride, int batch, int h, int w, int c, const float* scale,
+                                    const float* shift, float slope, int has_act, const void* residual, int res_cstride,
+                                    void* y, int y_cstride, const float* slope_dev, void* xs, int xs_cstride,
+                                    void* stream_) {
+  RYOLO_ARG_CHECK(xs != nullptr);
+  return bn_act_fwd_impl(z, z_cstride, batch, h, w, c, scale, shift, slope, has_act, residual, res_cstride, y, y_cstride, 0,
+                         slope_dev, xs, xs_cstride, stream_);
 }
 
 extern "C" int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, void* z_dz, int z_cstride, int batch, int h,
@@ -599,7 +629,8 @@ extern "C" int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(dy && z_dz && scale && shift && mean && invstd && sums);
   GEO_CHECK();
-  RYOLO_ARG_CHECK(!(gres && upsample2x));
+  RYOLO_ARG_CHECK(upsample2x >= 0 && upsample2x <= 2 && !(gres && upsample2x == 1));
+  RYOLO_ARG_CHECK(upsample2x != 2 || (h % 2 == 0 && w % 2 == 0 && dy_cstride >= 4 * c));
   GEO_CHECK_P2();
   const Geo g = mk_geo(batch, h, w, c);
   RYOLO_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * (2 * c + 1), stream));

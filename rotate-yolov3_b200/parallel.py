@@ -119,10 +119,14 @@ class DistributedDataParallel(torch.nn.Module):
     finished gradient buckets to GradBuckets, so the NCCL all-reduce of bucket k overlaps the backward kernels of the
     blocks before it; the gradients autograd receives are already averaged over the ranks."""
 
-    def __init__(self, module, bucket_mb=32, process_group=None, reserved_sms=8):
+    def __init__(self, module, bucket_mb=32, process_group=None, reserved_sms=0):
         super().__init__()
         self.module = module
-        # reserved_sms: SMs the backward GEMMs leave to the concurrent NCCL kernels (pair it with NCCL_MAX_NCHANNELS <= 8)
+        # reserved_sms: SMs the backward GEMMs leave to the concurrent NCCL kernels.  Measured at 2 GPUs (profiles/
+        # r02_n2_experiments.txt): 0 is best (41.2 ms/step; 8 reserved: 44-56 ms, the tile counts of the 19^2 / 38^2 layers at
+        # 32 images no longer fit whole waves of 140 CTAs), so the default leaves every SM to the GEMMs
+        import os
+        reserved_sms = int(os.environ.get("RYOLO_DDP_RESERVED_SMS", reserved_sms))     # measurement knob
         module._ddp = {"bucket_bytes": int(bucket_mb) << 20, "group": process_group, "reserved_sms": int(reserved_sms)}
         module._tplan = None          # the plan builds its buckets at construction
         module._pplan = None

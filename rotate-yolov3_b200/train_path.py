@@ -173,12 +173,21 @@ class TrainPlan:
                 raise NotImplementedError("%s at block %d does not follow a convolution it can be fused into" % (t, i))
             i += 1
         self.blocks = blocks
+        # a block whose output feeds a space-to-depth (3x3 / stride 2) block writes the s2d copy itself (bn_act_fwd_s2d)
+        for c_ in blocks:
+            c_.xs_from_producer = False
+        for c_ in blocks:
+            if c_.s2d:
+                prod = [p_ for p_ in blocks if not p_.is_head and p_.y is c_.src and not p_.fuse_up]
+                if len(prod) == 1:
+                    prod[0].xs_out = c_.xs
+                    c_.xs_from_producer = True
         self.zero_bias = torch.zeros(2048, dtype=torch.float32, device=device)
         # static accumulate flags for the backward writers (first writer of a gradient range overwrites)
         written = {}
 
         def claim(view):
-            key = view.buf.data_ptr()
+            key = id(view.buf)
             lo, hi = view.ch_off, view.ch_off + view.c
             covered = any(a <= lo and hi <= b for a, b in written.get(key, []))
             written.setdefault(key, []).append((lo, hi))
@@ -186,6 +195,20 @@ class TrainPlan:
         for blk in reversed(blocks):
             blk.gres_acc = claim(blk.gres) if blk.gres is not None else False
             blk.gsrc_acc = claim(blk.gsrc) if blk.gsrc is not None else False
+        # A producer whose output gradient has ONE writer -- the depth_to_space of its space-to-depth consumer -- reads that
+        # gradient straight from the consumer's dgrad output (bn_act_bwd mode 2): no d2s pass, no gy buffer traffic.
+        for c_ in blocks:
+            c_.dxs_direct = False
+        for c_ in blocks:
+            if not c_.s2d or c_.gsrc is None:
+                continue
+            key = id(c_.gsrc.buf)
+            lo, hi = c_.gsrc.ch_off, c_.gsrc.ch_off + c_.gsrc.c
+            writers = [r for r in written.get(key, []) if not (r[1] <= lo or hi <= r[0])]
+            prod = [p_ for p_ in blocks if not p_.is_head and p_.gy is c_.gsrc and not p_.fuse_up]
+            if len(writers) == 1 and len(prod) == 1:
+                prod[0].dy_s2d = c_
+                c_.dxs_direct = True
         self._build_arena()
         # split-K partial sums of every layer's weight gradient in ONE buffer: one fill per step instead of 75
         off = 0
@@ -371,8 +394,9 @@ class TrainPlan:
                 w = w.reshape(blk.cout, 27, 1, 1)
             x_ptr = blk.src.ptr
             if blk.s2d:
-                _lib.check(lib.ryolo_space_to_depth(ctypes.c_void_p(blk.src.ptr), blk.src.cs, self.batch, blk.src.h, blk.src.w,
-                                                    blk.src.c, _lib.ptr(blk.xs), blk.xs_cs, st), "s2d")
+                if not blk.xs_from_producer:
+                    _lib.check(lib.ryolo_space_to_depth(ctypes.c_void_p(blk.src.ptr), blk.src.cs, self.batch, blk.src.h,
+                                                        blk.src.w, blk.src.c, _lib.ptr(blk.xs), blk.xs_cs, st), "s2d")
                 x_ptr = blk.xs.data_ptr()
             if blk.is_head:
                 if getattr(blk, "bias_pad", None) is None:
@@ -396,6 +420,15 @@ class TrainPlan:
                 bn_counters.append(bn.num_batches_tracked)
             else:
                 raise NotImplementedError("conv block without BatchNorm that is not a YOLO head")
+            xs_out = getattr(blk, "xs_out", None)
+            if xs_out is not None:
+                _lib.check(lib.ryolo_bn_act_fwd_s2d(_lib.ptr(blk.z), blk.zcs, self.batch, blk.oh, blk.ow, blk.cout,
+                                                    _lib.ptr(blk.scale), _lib.ptr(blk.shift), blk.slope, int(blk.has_act),
+                                                    ctypes.c_void_p(blk.res.ptr) if blk.res is not None else None,
+                                                    blk.res.cs if blk.res is not None else 0, ctypes.c_void_p(blk.y.ptr),
+                                                    blk.y.cs, ctypes.c_void_p(blk.slope_dev), _lib.ptr(xs_out),
+                                                    xs_out.shape[-1], st), "bn_act_fwd_s2d")
+                continue
             _lib.check(lib.ryolo_bn_act_fwd(_lib.ptr(blk.z), blk.zcs, self.batch, blk.oh, blk.ow, blk.cout,
                                             _lib.ptr(blk.scale), _lib.ptr(blk.shift), blk.slope, int(blk.has_act),
                                             ctypes.c_void_p(blk.res.ptr) if blk.res is not None else None,
@@ -472,7 +505,10 @@ class TrainPlan:
         if blk.is_head:
             dz = blk.dz
         else:
-            _lib.check(lib.ryolo_bn_act_bwd(ctypes.c_void_p(blk.gy.ptr), blk.gy.cs, int(blk.fuse_up), _lib.ptr(blk.z),
+            src_c = getattr(blk, "dy_s2d", None)
+            dy_ptr, dy_cs, dy_mode = (blk.gy.ptr, blk.gy.cs, int(blk.fuse_up)) if src_c is None else \
+                (src_c.dxs.data_ptr(), src_c.xs_cs, 2)
+            _lib.check(lib.ryolo_bn_act_bwd(ctypes.c_void_p(dy_ptr), dy_cs, dy_mode, _lib.ptr(blk.z),
                                             blk.zcs, self.batch, blk.oh, blk.ow, blk.cout, _lib.ptr(blk.scale),
                                             _lib.ptr(blk.shift), _lib.ptr(blk.mean), _lib.ptr(blk.invstd), blk.slope,
                                             int(blk.has_act), 1, _lib.ptr(blk.bsums),
@@ -487,8 +523,9 @@ class TrainPlan:
                                             st), "wgrad s2d")
             _lib.check(lib.ryolo_conv_bn_act_fwd(ctypes.byref(blk.ddesc), _lib.ptr(dz), _lib.ptr(blk.pwd),
                                                  _lib.ptr(self.zero_bias), None, _lib.ptr(blk.dxs), None, 0, st), "dgrad s2d")
-            _lib.check(lib.ryolo_depth_to_space(_lib.ptr(blk.dxs), blk.xs_cs, self.batch, blk.src.h, blk.src.w, blk.src.c,
-                                                ctypes.c_void_p(blk.gsrc.ptr), blk.gsrc.cs, int(blk.gsrc_acc), st), "d2s")
+            if not blk.dxs_direct:
+                _lib.check(lib.ryolo_depth_to_space(_lib.ptr(blk.dxs), blk.xs_cs, self.batch, blk.src.h, blk.src.w, blk.src.c,
+                                                    ctypes.c_void_p(blk.gsrc.ptr), blk.gsrc.cs, int(blk.gsrc_acc), st), "d2s")
             return
         if blk.stride == 2:
             _lib.check(lib.ryolo_zero_insert2x(_lib.ptr(dz), blk.zcs, self.batch, blk.oh, blk.ow, blk.zcs,
@@ -510,7 +547,7 @@ class TrainPlan:
         if overlap:
             # leave a few SMs to the NCCL all-reduce kernels that run next to the backward GEMMs (persistent kernels with a
             # static tile schedule would otherwise run a second wave on the SMs NCCL occupies)
-            _lib.lib.ryolo_set_reserved_sms(int(getattr(m, "_ddp", {}).get("reserved_sms", 8)))
+            _lib.lib.ryolo_set_reserved_sms(int(getattr(m, "_ddp", {}).get("reserved_sms", 0)))
         try:
             return self._backward(grads)
         finally:
