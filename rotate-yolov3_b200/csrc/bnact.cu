@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "f32x2.cuh"
+#include "tc05.cuh"
 
 namespace ryolo {
 
@@ -567,6 +568,8 @@ static inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 }  // namespace ryolo
 
+#include "bnpipe.cuh"
+
 using namespace ryolo;
 
 #define GEO_CHECK() RYOLO_ARG_CHECK(batch > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && c <= 2048)
@@ -579,6 +582,16 @@ extern "C" int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, in
   const Geo g = mk_geo(batch, h, w, c);
   RYOLO_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, stream));
   GEO_CHECK_P2();
+  if (pipe_ok(g, z_cstride)) {
+    int grid;
+    const PieceGeo pg = mk_pieces(g, &grid);
+    constexpr size_t kMax = RowPipe<1, 4>::smem_bytes() + (2 * 2048 + 1) * sizeof(float);
+    RYOLO_SMEM_OPT_IN(bn_stats_pipe_kernel, kMax);
+    bn_stats_pipe_kernel<<<grid, BNT, RowPipe<1, 4>::smem_bytes() + 2 * c * sizeof(float), stream>>>(
+        static_cast<const __nv_bfloat16*>(z), g, pg, sums);
+    RYOLO_LAUNCH_CHECK();
+    return RYOLO_OK;
+  }
   const int rpb = rows_per_block(g);
   const unsigned blocks = (unsigned)((batch * h + rpb - 1) / rpb);
   bn_stats_kernel<<<blocks, BNT, 2 * c * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(z), z_cstride, g, sums,
@@ -597,6 +610,17 @@ static int bn_act_fwd_impl(const void* z, int z_cstride, int batch, int h, int w
   RYOLO_ARG_CHECK(!xs || (!upsample2x && h % 2 == 0 && w % 2 == 0 && xs_cstride >= 4 * c && xs_cstride % 8 == 0));
   GEO_CHECK_P2();
   const Geo g = mk_geo(batch, h, w, c);
+  if (pipe_ok(g, z_cstride)) {
+    int grid;
+    const PieceGeo pg = mk_pieces(g, &grid);
+    RYOLO_SMEM_OPT_IN(bn_act_fwd_pipe_kernel, (RowPipe<1, 4>::smem_bytes()));
+    bn_act_fwd_pipe_kernel<<<grid, BNT, RowPipe<1, 4>::smem_bytes(), stream>>>(
+        static_cast<const __nv_bfloat16*>(z), g, pg, scale, shift, slope, has_act, static_cast<const __nv_bfloat16*>(residual),
+        res_cstride, static_cast<__nv_bfloat16*>(y), y_cstride, upsample2x, slope_dev, static_cast<__nv_bfloat16*>(xs),
+        xs_cstride);
+    RYOLO_LAUNCH_CHECK();
+    return RYOLO_OK;
+  }
   const int rpb = rows_per_block(g);
   bn_act_fwd_kernel<<<(unsigned)((batch * h + rpb - 1) / rpb), BNT, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(z), z_cstride, g, scale, shift, slope, has_act,
@@ -634,6 +658,40 @@ extern "C" int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, 
   GEO_CHECK_P2();
   const Geo g = mk_geo(batch, h, w, c);
   RYOLO_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * (2 * c + 1), stream));
+  const float inv_cnt = 1.0f / ((float)batch * h * w);
+  if (pipe_ok(g, z_cstride)) {
+    int grid;
+    const PieceGeo pg = mk_pieces(g, &grid);
+    const bool dyp = upsample2x == 0 && dy_cstride == c;
+    constexpr size_t kPipe = RowPipe<2, 2>::smem_bytes();
+    static_assert(RowPipe<2, 2>::smem_bytes() == RowPipe<1, 4>::smem_bytes() - 16, "stage rings of equal size");
+    constexpr size_t kMax = RowPipe<1, 4>::smem_bytes() + (2 * 2048 + 1) * sizeof(float);
+    const size_t red_bytes = (dyp ? kPipe : RowPipe<1, 4>::smem_bytes()) + (2 * c + 1) * sizeof(float);
+    const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
+    __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(z_dz);
+    __nv_bfloat16* grb = static_cast<__nv_bfloat16*>(gres);
+    if (dyp) {
+      RYOLO_SMEM_OPT_IN(bn_act_bwd_reduce_pipe_kernel<1>, kMax);
+      RYOLO_SMEM_OPT_IN(bn_act_bwd_apply_pipe_kernel<1>, kMax);
+      bn_act_bwd_reduce_pipe_kernel<1><<<grid, BNT, red_bytes, stream>>>(dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean,
+                                                                      invstd, slope, has_act, sums, slope_dev);
+      RYOLO_LAUNCH_CHECK();
+      bn_act_bwd_apply_pipe_kernel<1><<<grid, BNT, kPipe, stream>>>(dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean,
+                                                                 invstd, slope, has_act, has_bn, sums, inv_cnt, grb,
+                                                                 gres_cstride, gres_accumulate, slope_dev);
+    } else {
+      RYOLO_SMEM_OPT_IN(bn_act_bwd_reduce_pipe_kernel<0>, kMax);
+      RYOLO_SMEM_OPT_IN(bn_act_bwd_apply_pipe_kernel<0>, kMax);
+      bn_act_bwd_reduce_pipe_kernel<0><<<grid, BNT, red_bytes, stream>>>(dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean,
+                                                                      invstd, slope, has_act, sums, slope_dev);
+      RYOLO_LAUNCH_CHECK();
+      bn_act_bwd_apply_pipe_kernel<0><<<grid, BNT, RowPipe<1, 4>::smem_bytes(), stream>>>(
+          dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean, invstd, slope, has_act, has_bn, sums, inv_cnt, grb,
+          gres_cstride, gres_accumulate, slope_dev);
+    }
+    RYOLO_LAUNCH_CHECK();
+    return RYOLO_OK;
+  }
   const int rpb = rows_per_block(g);
   const unsigned blocks = (unsigned)((batch * h + rpb - 1) / rpb);
   bn_act_bwd_reduce_kernel<<<blocks, BNT, (2 * c + 1) * sizeof(float), stream>>>(

@@ -23,6 +23,8 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "f32x2.cuh"
+#include "riou_area.cuh"
 
 namespace ryolo {
 
@@ -147,21 +149,59 @@ __global__ void __launch_bounds__(256) riou_paired_kernel(const float* __restric
   out[i] = r;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pairwise kernel, round 2.  A CTA owns a strip of CT = 128 columns (their derived data -- sincosf included -- is computed
+// once) and walks ROW_TILES row tiles of RT = 32 rows; per 32 x 128 tile:
+//   A1  bounding circles for all 4096 pairs with PACKED fp32x2 math, two rows per instruction: d^2 - R^2 from 7 packed
+//       ops per 2 pairs, its sign bit shifted into a 16-bit pass mask by one funnel shift per pair (no compare, no
+//       predicate) -- 5.5 instructions per pair (round 1: 23).  Survivors (~28 %) -> queue 1.
+//   A2  separating axes on queue 1 in converged warps (branch-free, one comparison) -> queue 2 (~12 %).
+//   B   clamp integral (riou_area.cuh, ~140 instructions, round 1: ~350) on queue 2 -> output tile in shared memory.
+//   W   the tile goes out with 128-bit streaming stores and is re-zeroed in the same pass; warp 0 derives the next row
+//       tile's boxes meanwhile.
+// Invalid boxes (non-finite or zero area: IoU 0 with everything, utils/utils.py:669-673) are moved to x = +-1e18 so that the
+// circle test rejects them without a flag.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ROW_TILES = 8;
+
 struct RiouSmem {
-  float4 row0[RT], row1[RT];   // (cx, cy, rad, area), (c, s, hw, hh)
-  float4 col0[CT], col1[CT];
+  float4 col0[CT], col1[CT];   // (cx, cy, 1.0001 rad, area), (c, s, hw, hh)
+  float4 row0[RT], row1[RT];
+  float4 rnxy[RT / 2];         // (-x[2j], -x[2j+1], -y[2j], -y[2j+1])
+  float4 rrr[RT / 2];          // (R[2j], R[2j+1], -R[2j], -R[2j+1]),  R = 1.0001 rad
   float out[RT * CT];
   unsigned short q1[RT * CT];
   unsigned short q2[RT * CT];
   int cnt1, cnt2;
 };
 
-__device__ __forceinline__ RBox load_rbox(const float4* p0, const float4* p1, int i) {
-  const float4 u = p0[i], v = p1[i];
-  RBox b;
-  b.cx = u.x; b.cy = u.y; b.rad = u.z; b.area = u.w;
-  b.c = v.x; b.s = v.y; b.hw = v.z; b.hh = v.w;
-  return b;
+constexpr float FAR_AWAY = 1e18f;
+
+__device__ __forceinline__ void derive_box(const float* __restrict__ p, bool in_range, float far, float4& d0, float4& d1) {
+  RBox bx;
+  bool live = false;
+  if (in_range) {
+    bx = make_rbox(p);
+    live = bx.rad >= 0.f;
+  }
+  if (live) {
+    d0 = make_float4(bx.cx, bx.cy, bx.rad * 1.0001f, bx.area);
+    d1 = make_float4(bx.c, bx.s, bx.hw, bx.hh);
+  } else {
+    d0 = make_float4(far, 0.f, 0.f, 0.f);
+    d1 = make_float4(1.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ void store_row(RiouSmem& sm, int t, const float4& d0, const float4& d1) {
+  sm.row0[t] = d0;
+  sm.row1[t] = d1;
+  float* nxy = reinterpret_cast<float*>(sm.rnxy) + (t >> 1) * 4 + (t & 1);
+  nxy[0] = -d0.x;
+  nxy[2] = -d0.y;
+  float* rr = reinterpret_cast<float*>(sm.rrr) + (t >> 1) * 4 + (t & 1);
+  rr[0] = d0.z;
+  rr[2] = -d0.z;
 }
 
 template <int STORE>   // 0: streaming (st.global.cs), 1: plain, 2: write-through (st.global.wt)
@@ -170,113 +210,172 @@ __global__ void __launch_bounds__(RIOU_THREADS, 4) riou_pairwise_kernel(const fl
                                                                         int mode, float* __restrict__ out) {
   __shared__ RiouSmem sm;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int r0 = blockIdx.y * RT, c0 = blockIdx.x * CT;
+  const int c0 = blockIdx.x * CT;
+  const int tile0 = blockIdx.y * ROW_TILES;
+  const int n_tiles = min(ROW_TILES, (n + RT - 1) / RT - tile0);
 
   if (tid < RT) {
-    RBox bx;
-    if (r0 + tid < n) bx = make_rbox(a + (size_t)(r0 + tid) * sa);
-    else { bx = RBox{}; bx.rad = -1.f; }
-    sm.row0[tid] = make_float4(bx.cx, bx.cy, bx.rad, bx.area);
-    sm.row1[tid] = make_float4(bx.c, bx.s, bx.hw, bx.hh);
+    float4 d0, d1;
+    const int r = tile0 * RT + tid;
+    derive_box(a + (size_t)r * sa, r < n, FAR_AWAY, d0, d1);
+    store_row(sm, tid, d0, d1);
   } else if (tid >= 64 && tid < 64 + CT) {
     const int j = tid - 64;
-    RBox bx;
-    if (c0 + j < m) bx = make_rbox(b + (size_t)(c0 + j) * sb);
-    else { bx = RBox{}; bx.rad = -1.f; }
-    sm.col0[j] = make_float4(bx.cx, bx.cy, bx.rad, bx.area);
-    sm.col1[j] = make_float4(bx.c, bx.s, bx.hw, bx.hh);
+    float4 d0, d1;
+    derive_box(b + (size_t)(c0 + j) * sb, c0 + j < m, -FAR_AWAY, d0, d1);
+    sm.col0[j] = d0;
+    sm.col1[j] = d1;
   }
   if (tid == 0) { sm.cnt1 = 0; sm.cnt2 = 0; }
-  {  // pre-zero the output tile: 4096 floats = 1024 float4
+  {  // zero the output tile once; the write-back pass re-zeroes what it reads
     float4* o4 = reinterpret_cast<float4*>(sm.out);
 #pragma unroll
     for (int e = 0; e < (RT * CT / 4) / RIOU_THREADS; e++) o4[tid + e * RIOU_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
 
-  // ---- stage A1: bounding circles; thread = one column x 16 rows ----
-  {
-    const int c = tid & (CT - 1);
-    const int rg = tid >> 7;
-    const float4 cb = sm.col0[c];
-    unsigned pass = 0;
-    if (cb.z >= 0.f) {
+  const int cols = min(CT, m - c0);
+  const bool vec_store = (m & 3) == 0 && cols == CT && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+
+#pragma unroll 1
+  for (int t = 0; t < n_tiles; t++) {
+    const int r0 = (tile0 + t) * RT;
+    // ---- stage A1: bounding circles; thread = one column x 16 rows, two rows per packed instruction ----
+    {
+      const int c = tid & (CT - 1);
+      const int rg = tid >> 7;
+      const float4 cb = sm.col0[c];
+      const uint64_t cx2 = f2pack(cb.x, cb.x), cy2 = f2pack(cb.y, cb.y), cr2 = f2pack(cb.z, cb.z), crn2 = f2pack(-cb.z, -cb.z);
+      unsigned pass = 0;
 #pragma unroll
-      for (int k = 0; k < RT / 2; k++) {
-        const float4 rb = sm.row0[rg * (RT / 2) + k];   // broadcast
-        const float dx = cb.x - rb.x, dy = cb.y - rb.y;
-        const float R = (cb.z + rb.z) * 1.0001f;
-        const bool ok = rb.z >= 0.f && !(fmaf(dx, dx, dy * dy) > R * R);
-        pass |= (ok ? 1u : 0u) << k;
+      for (int j = 0; j < RT / 4; j++) {
+        const float4 xy = sm.rnxy[rg * (RT / 4) + j];   // broadcast
+        const float4 rr = sm.rrr[rg * (RT / 4) + j];
+        const uint64_t dx = f2add(cx2, f2pack(xy.x, xy.y));
+        const uint64_t dy = f2add(cy2, f2pack(xy.z, xy.w));
+        const uint64_t R = f2add(cr2, f2pack(rr.x, rr.y));
+        const uint64_t Rn = f2add(crn2, f2pack(rr.z, rr.w));
+        uint64_t s = f2mul(dy, dy);
+        s = f2fma(dx, dx, s);
+        s = f2fma(R, Rn, s);       // d^2 - R^2 : negative <=> the circles overlap
+        float s0, s1;
+        f2unpack(s, s0, s1);
+        pass = __funnelshift_l(__float_as_uint(s0), pass, 1);
+        pass = __funnelshift_l(__float_as_uint(s1), pass, 1);
       }
-    }
-    // one compaction per thread: warp exclusive scan of the counts + one atomic per warp
-    const int cnt = __popc(pass);
-    int incl = cnt;
+      // row k of this thread's 16 sits in bit 15 - k.  One compaction per thread: warp scan of the counts, one atomic
+      const int cnt = __popc(pass);
+      int incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    int base = 0;
-    if (lane == 31) base = atomicAdd(&sm.cnt1, incl);
-    base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-    while (pass) {
-      const int k = __ffs(pass) - 1;
-      pass &= pass - 1;
-      sm.q1[base++] = (unsigned short)(((rg * (RT / 2) + k) << 7) | c);
-    }
-  }
-  __syncthreads();
-  // ---- stage A2: separating axes on queue 1 (converged warps) ----
-  {
-    const int cnt1 = sm.cnt1;
-    for (int q0 = 0; q0 < cnt1; q0 += RIOU_THREADS) {
-      const int q = q0 + tid;
-      bool keep = false;
-      int e = 0;
-      if (q < cnt1) {
-        e = sm.q1[q];
-        const RBox ra = load_rbox(sm.row0, sm.row1, e >> 7), cb = load_rbox(sm.col0, sm.col1, e & (CT - 1));
-        keep = !sat_disjoint(ra, cb);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
       }
-      const unsigned mk = __ballot_sync(0xffffffffu, keep);
-      if (mk) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sm.cnt2, __popc(mk));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) sm.q2[base + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)e;
+      int base = 0;
+      if (lane == 31) base = atomicAdd(&sm.cnt1, incl);
+      base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+      const int row_hi = rg * (RT / 2) + 15;
+      while (pass) {
+        const int bp = 31 - __clz(pass);
+        pass ^= 1u << bp;
+        sm.q1[base++] = (unsigned short)(((row_hi - bp) << 7) | c);
+      }
+      if (tid == 0) sm.cnt2 = 0;
+    }
+    __syncthreads();
+    // ---- stage A2: separating axes on queue 1 (converged warps, branch-free); ONE compaction per thread ----
+    {
+      const int cnt1 = sm.cnt1;
+      unsigned kept = 0;               // bit i: my entry of round i (queue index i * 256 + tid) survives
+#pragma unroll 1
+      for (int q = tid, round = 0; q < cnt1; q += RIOU_THREADS, round++) {
+        const int e = sm.q1[q];
+        const float4 a0 = sm.row0[e >> 7], a1 = sm.row1[e >> 7], b0 = sm.col0[e & (CT - 1)], b1 = sm.col1[e & (CT - 1)];
+        const float dx = b0.x - a0.x, dy = b0.y - a0.y;
+        const float rx = fmaf(dx, a1.x, dy * a1.y), ry = fmaf(dy, a1.x, -dx * a1.y);      // offset in a's frame
+        const float cd = fmaf(a1.x, b1.x, a1.y * b1.y), sd = fmaf(a1.x, b1.y, -a1.y * b1.x);
+        const float px = fmaf(rx, cd, ry * sd), py = fmaf(ry, cd, -rx * sd);              // offset in b's frame
+        const float C = fabsf(cd), S = fabsf(sd);
+        const float k = -1.0001f;      // tiny relative slack: touching boxes go on to the integral
+        const float m1 = fmaf(k, fmaf(b1.w, S, fmaf(b1.z, C, a1.z)), fabsf(rx));
+        const float m2 = fmaf(k, fmaf(b1.w, C, fmaf(b1.z, S, a1.w)), fabsf(ry));
+        const float m3 = fmaf(k, fmaf(a1.w, S, fmaf(a1.z, C, b1.z)), fabsf(px));
+        const float m4 = fmaf(k, fmaf(a1.w, C, fmaf(a1.z, S, b1.w)), fabsf(py));
+        const float worst = fmaxf(fmaxf(m1, m2), fmaxf(m3, m4));      // > 0: separated on some axis
+        kept |= (worst > 0.f ? 0u : 1u) << round;
+      }
+      const int cnt = __popc(kept);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      int base = 0;
+      if (lane == 31 && incl) base = atomicAdd(&sm.cnt2, incl);
+      base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+      while (kept) {
+        const int round = __ffs(kept) - 1;
+        kept &= kept - 1;
+        sm.q2[base++] = sm.q1[round * RIOU_THREADS + tid];
       }
     }
-  }
-  __syncthreads();
-  // ---- stage B: clamp integral on queue 2 ----
-  {
-    const int cnt2 = sm.cnt2;
-    for (int q = tid; q < cnt2; q += RIOU_THREADS) {
-      const int e = sm.q2[q];
-      const int r = e >> 7, c = e & (CT - 1);
-      const RBox ra = load_rbox(sm.row0, sm.row1, r), cb = load_rbox(sm.col0, sm.col1, c);
-      sm.out[r * CT + c] = iou_from_inter(ra, cb, clamp_integral_area(ra, cb), mode);
+    __syncthreads();
+    // ---- stage B: clamp integral on queue 2 ----
+    {
+      const int cnt2 = sm.cnt2;
+      if (tid == 0) sm.cnt1 = 0;      // queue 1 is consumed
+      for (int q = tid; q < cnt2; q += RIOU_THREADS) {
+        const int e = sm.q2[q];
+        const int r = e >> 7, c = e & (CT - 1);
+        const float4 a0 = sm.row0[r], a1 = sm.row1[r], b0 = sm.col0[c], b1 = sm.col1[c];
+        float inter = clamp_integral_area2(a0.x, a0.y, a1.x, a1.y, a1.z, a1.w, b0.x, b0.y, b1.x, b1.y, b1.z, b1.w);
+        inter = fminf(inter, fminf(a0.w, b0.w));
+        float uni = a0.w + b0.w - inter;
+        if (mode == RYOLO_IOU_MODE_GIOU) {
+          RBox ra, rb;
+          ra.cx = a0.x; ra.cy = a0.y; ra.c = a1.x; ra.s = a1.y; ra.hw = a1.z; ra.hh = a1.w;
+          rb.cx = b0.x; rb.cy = b0.y; rb.c = b1.x; rb.s = b1.y; rb.hw = b1.z; rb.hh = b1.w;
+          uni = envelope_area(ra, rb);
+        }
+        sm.out[r * CT + c] = uni == 0.f ? 0.f : inter / uni;   // union == 0 -> 0 (utils/utils.py:693-694)
+      }
     }
-  }
-  __syncthreads();
-  // ---- write back ----
-  const int rows = min(RT, n - r0), cols = min(CT, m - c0);
-  if ((m & 3) == 0 && cols == CT && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    for (int e = tid; e < rows * (CT / 4); e += RIOU_THREADS) {
-      const int r = e / (CT / 4), c4 = e % (CT / 4);
-      const float4 v = *reinterpret_cast<const float4*>(&sm.out[r * CT + c4 * 4]);
-      float4* dst = reinterpret_cast<float4*>(out + (size_t)(r0 + r) * m + c0 + c4 * 4);
-      if (STORE == 0) __stcs(dst, v);        // streaming: the matrix is written once and not re-read by this kernel
-      else if (STORE == 1) *dst = v;
-      else __stwt(dst, v);
+    __syncthreads();
+    // ---- write back (and re-zero); warp 0 first derives the next row tile ----
+    if (tid < RT && t + 1 < n_tiles) {
+      float4 d0, d1;
+      const int r = r0 + RT + tid;
+      derive_box(a + (size_t)r * sa, r < n, FAR_AWAY, d0, d1);
+      store_row(sm, tid, d0, d1);
     }
-  } else {
-    for (int e = tid; e < rows * CT; e += RIOU_THREADS) {
-      const int r = e / CT, c = e % CT;
-      if (c < cols) out[(size_t)(r0 + r) * m + c0 + c] = sm.out[r * CT + c];
+    const int rows = min(RT, n - r0);
+    if (vec_store) {
+      // thread = (row tid/32 + 8k, columns 4*(tid%32) ..): one LDS.128 + STS.128 + STG.128 per 4 pairs
+      const int c4 = tid & 31;
+      float4* src = reinterpret_cast<float4*>(sm.out) + tid;
+      float4* dst = reinterpret_cast<float4*>(out + (size_t)(r0 + (tid >> 5)) * m + c0) + c4;
+      const size_t dstep = (size_t)(RIOU_THREADS / 32) * m / 4;
+#pragma unroll
+      for (int k = 0; k < RT / (RIOU_THREADS / 32); k++) {
+        if ((tid >> 5) + k * (RIOU_THREADS / 32) < rows) {
+          const float4 v = src[k * RIOU_THREADS];
+          src[k * RIOU_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4* d = dst + k * dstep;
+          if (STORE == 0) __stcs(d, v);        // streaming: the matrix is written once and not re-read by this kernel
+          else if (STORE == 1) *d = v;
+          else __stwt(d, v);
+        }
+      }
+    } else {
+      for (int e = tid; e < rows * CT; e += RIOU_THREADS) {
+        const int r = e / CT, c = e % CT;
+        const float v = sm.out[r * CT + c];
+        sm.out[r * CT + c] = 0.f;
+        if (c < cols) out[(size_t)(r0 + r) * m + c0 + c] = v;
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -303,7 +402,7 @@ extern "C" int ryolo_riou_pairwise(const float* a, int n, int stride_a, const fl
   RYOLO_ARG_CHECK(mode == RYOLO_IOU_MODE_IOU || mode == RYOLO_IOU_MODE_GIOU);
   if (n == 0 || m == 0) return RYOLO_OK;
   RYOLO_ARG_CHECK(a && b && out);
-  dim3 grid((m + CT - 1) / CT, (n + RT - 1) / RT);
+  dim3 grid((m + CT - 1) / CT, ((n + RT - 1) / RT + ROW_TILES - 1) / ROW_TILES);
   RYOLO_ARG_CHECK(grid.y <= 65535);
   static int store_mode = -1;
   if (store_mode < 0) {   // measurement knob (profiles/): RYOLO_RIOU_STORE=0|1|2, default streaming stores
