@@ -349,6 +349,20 @@ int ryolo_nchw_to_padded(const float* src, int batch, int c, int h, int w, void*
  * with channel = a*no + k (the head conv's filter index); channels >= na*no are left untouched. */
 int ryolo_head_grad_to_padded(const float* g, int batch, int na, int no, int ny, int nx, void* dst,
                               int dst_cstride, void* stream);
+/* Same, for the cotangent in the layout the head convolution WROTE its output in: fp32 NCHW [B, C = na*no, ny, nx]
+ * (what arrives when the consumer differentiates the permuted VIEW of that buffer, e.g. the fused loss below). */
+int ryolo_head_grad_nchw_to_padded(const float* g, int batch, int c, int ny, int nx, void* dst,
+                                   int dst_cstride, void* stream);
+/* Objectness term of compute_loss (reference model/loss.py:340-348: BCEWithLogitsLoss(pos_weight)(pi[..., 5], tobj)
+ * over every cell of a head map).  x: logical [batch, na, ny, nx, no] fp32 tensor addressed through `strides` (5 element
+ * strides, so both the contiguous tensor and the permuted view of the NCHW head buffer are read in place); ch = the
+ * objectness channel; tobj: contiguous [batch, na, ny, nx].  fwd ADDS the sum of the element losses to *sum_out
+ * (float64, caller zeroes it and divides by the cell count); bwd writes the whole cotangent tensor `grad` (strides of x):
+ * channel ch = *scale_dev * d(loss)/dx, every other channel 0. */
+int ryolo_obj_bce_fwd(const float* x, const long long* strides, int batch, int na, int ny, int nx, int no, int ch,
+                      const float* tobj, float pos_weight, double* sum_out, void* stream);
+int ryolo_obj_bce_bwd(const float* x, const long long* strides, int batch, int na, int ny, int nx, int no, int ch,
+                      const float* tobj, float pos_weight, const float* scale_dev, float* grad, void* stream);
 /* im2col of the 3-channel fp32 image for the first 3x3 conv: bf16 padded NHWC with 64 channels
  * (27 real, column = c*9 + kh*3 + kw), so that the first layer runs on the same GEMM kernels. */
 int ryolo_im2col_first(const float* img, int batch, int h, int w, void* dst, void* stream);

@@ -582,7 +582,7 @@ extern "C" int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, in
   const Geo g = mk_geo(batch, h, w, c);
   RYOLO_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, stream));
   GEO_CHECK_P2();
-  if (pipe_ok(g, z_cstride)) {
+  if (pipe_ok(g, z_cstride, PIPE_STATS)) {
     int grid;
     const PieceGeo pg = mk_pieces(g, &grid);
     constexpr size_t kMax = RowPipe<1, 4>::smem_bytes() + (2 * 2048 + 1) * sizeof(float);
@@ -610,7 +610,7 @@ static int bn_act_fwd_impl(const void* z, int z_cstride, int batch, int h, int w
   RYOLO_ARG_CHECK(!xs || (!upsample2x && h % 2 == 0 && w % 2 == 0 && xs_cstride >= 4 * c && xs_cstride % 8 == 0));
   GEO_CHECK_P2();
   const Geo g = mk_geo(batch, h, w, c);
-  if (pipe_ok(g, z_cstride)) {
+  if (pipe_ok(g, z_cstride, PIPE_FWD)) {
     int grid;
     const PieceGeo pg = mk_pieces(g, &grid);
     RYOLO_SMEM_OPT_IN(bn_act_fwd_pipe_kernel, (RowPipe<1, 4>::smem_bytes()));
@@ -659,37 +659,36 @@ extern "C" int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, 
   const Geo g = mk_geo(batch, h, w, c);
   RYOLO_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * (2 * c + 1), stream));
   const float inv_cnt = 1.0f / ((float)batch * h * w);
-  if (pipe_ok(g, z_cstride)) {
+  if (pipe_ok(g, z_cstride, PIPE_BWD)) {
+    // how dy reaches the kernels: 1 = plain tensor on the pipe, 2 = space-to-depth dgrad output on the pipe (row pairs),
+    // 0 = direct loads (upsample adjoint, concat buffers)
+    const int dyp = (upsample2x == 0 && dy_cstride == c) ? 1
+                    : (upsample2x == 2 && dy_cstride == 4 * c && (c >> 3) * 2 <= PIPE_ITEMS / 2) ? 2 : 0;
     int grid;
-    const PieceGeo pg = mk_pieces(g, &grid);
-    const bool dyp = upsample2x == 0 && dy_cstride == c;
-    constexpr size_t kPipe = RowPipe<2, 2>::smem_bytes();
-    static_assert(RowPipe<2, 2>::smem_bytes() == RowPipe<1, 4>::smem_bytes() - 16, "stage rings of equal size");
-    constexpr size_t kMax = RowPipe<1, 4>::smem_bytes() + (2 * 2048 + 1) * sizeof(float);
-    const size_t red_bytes = (dyp ? kPipe : RowPipe<1, 4>::smem_bytes()) + (2 * c + 1) * sizeof(float);
+    const PieceGeo pg = mk_pieces(g, &grid, dyp == 2 ? 2 : 1);
+    constexpr size_t kMax = BwdPipe<0>::smem_bytes() + (2 * 2048 + 1) * sizeof(float);
+    static_assert(BwdPipe<0>::smem_bytes() == BwdPipe<1>::smem_bytes() + 16 && BwdPipe<1>::smem_bytes() == BwdPipe<2>::smem_bytes(),
+                  "stage rings of equal size");
     const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
     __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(z_dz);
     __nv_bfloat16* grb = static_cast<__nv_bfloat16*>(gres);
-    if (dyp) {
-      RYOLO_SMEM_OPT_IN(bn_act_bwd_reduce_pipe_kernel<1>, kMax);
-      RYOLO_SMEM_OPT_IN(bn_act_bwd_apply_pipe_kernel<1>, kMax);
-      bn_act_bwd_reduce_pipe_kernel<1><<<grid, BNT, red_bytes, stream>>>(dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean,
-                                                                      invstd, slope, has_act, sums, slope_dev);
-      RYOLO_LAUNCH_CHECK();
-      bn_act_bwd_apply_pipe_kernel<1><<<grid, BNT, kPipe, stream>>>(dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean,
-                                                                 invstd, slope, has_act, has_bn, sums, inv_cnt, grb,
-                                                                 gres_cstride, gres_accumulate, slope_dev);
-    } else {
-      RYOLO_SMEM_OPT_IN(bn_act_bwd_reduce_pipe_kernel<0>, kMax);
-      RYOLO_SMEM_OPT_IN(bn_act_bwd_apply_pipe_kernel<0>, kMax);
-      bn_act_bwd_reduce_pipe_kernel<0><<<grid, BNT, red_bytes, stream>>>(dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean,
-                                                                      invstd, slope, has_act, sums, slope_dev);
-      RYOLO_LAUNCH_CHECK();
-      bn_act_bwd_apply_pipe_kernel<0><<<grid, BNT, RowPipe<1, 4>::smem_bytes(), stream>>>(
-          dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean, invstd, slope, has_act, has_bn, sums, inv_cnt, grb,
-          gres_cstride, gres_accumulate, slope_dev);
-    }
-    RYOLO_LAUNCH_CHECK();
+    const size_t acc_bytes = (2 * c + 1) * sizeof(float);
+#define RYOLO_BWD_PIPE(D)                                                                                                  \
+  do {                                                                                                                   \
+    RYOLO_SMEM_OPT_IN(bn_act_bwd_reduce_pipe_kernel<D>, kMax);                                                           \
+    RYOLO_SMEM_OPT_IN(bn_act_bwd_apply_pipe_kernel<D>, kMax);                                                            \
+    bn_act_bwd_reduce_pipe_kernel<D><<<grid, BNT, BwdPipe<D>::smem_bytes() + acc_bytes, stream>>>(                       \
+        dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean, invstd, slope, has_act, sums, slope_dev);           \
+    RYOLO_LAUNCH_CHECK();                                                                                                \
+    bn_act_bwd_apply_pipe_kernel<D><<<grid, BNT, BwdPipe<D>::smem_bytes(), stream>>>(                                    \
+        dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean, invstd, slope, has_act, has_bn, sums, inv_cnt, grb,  \
+        gres_cstride, gres_accumulate, slope_dev);                                                                       \
+    RYOLO_LAUNCH_CHECK();                                                                                                \
+  } while (0)
+    if (dyp == 1) RYOLO_BWD_PIPE(1);
+    else if (dyp == 2) RYOLO_BWD_PIPE(2);
+    else RYOLO_BWD_PIPE(0);
+#undef RYOLO_BWD_PIPE
     return RYOLO_OK;
   }
   const int rpb = rows_per_block(g);

@@ -191,8 +191,91 @@ __global__ void __launch_bounds__(BNT, 2) bn_act_fwd_pipe_kernel(const __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// DYP = 1: dy is a plain tensor with channel stride == c and rides the pipe next to z; DYP = 0: dy comes through load_dy
-// (upsample adjoint, space-to-depth layout, or a concat buffer with a wider channel stride)
+// Backward passes.  Where dy comes from:
+//   DYP = 0  through load_dy (upsample adjoint, or a concat buffer with a wider channel stride): only z rides the pipe;
+//   DYP = 1  a plain tensor with channel stride == c: rides the pipe next to z (stage = z piece + dy piece);
+//   DYP = 2  the space-to-depth dgrad output of a following 3x3/stride-2 block (channel stride == 4c): ONE s2d row holds the
+//            dy of TWO image rows, so a piece is a ROW PAIR: stage = z piece of row 2k, z piece of row 2k+1 (10 KB each) and
+//            the matching run of the s2d row (20 KB, contiguous).  These are the three largest tensors of the network
+//            (608^2 x 32, 304^2 x 64, 152^2 x 128); through load_dy they ran at ~3 TB/s (profiles/r02d_launches_train_b64).
+template <int DYP>
+struct BwdPipe {
+  static constexpr int NST = DYP == 0 ? 4 : 2;
+  static constexpr int Z_ITEMS = DYP == 2 ? PIPE_ITEMS / 2 : PIPE_ITEMS;          // 16-byte items of one z piece
+  static constexpr int STAGE_ITEMS = DYP == 0 ? PIPE_ITEMS : 2 * PIPE_ITEMS;
+  static constexpr int ROWS = DYP == 2 ? 2 : 1;                                    // image rows per piece
+  static constexpr size_t smem_bytes() { return (size_t)NST * STAGE_ITEMS * 16 + 8 * NST; }
+
+  uint32_t buf0, bar0;
+  const uint4* gen;
+  int p_begin, p_end;
+  const __nv_bfloat16 *z, *dy;
+
+  __device__ __forceinline__ void init(unsigned char* smem, const PieceGeo& pg, const __nv_bfloat16* z_,
+                                       const __nv_bfloat16* dy_) {
+    buf0 = (uint32_t)__cvta_generic_to_shared(smem);
+    bar0 = buf0 + NST * STAGE_ITEMS * 16;
+    gen = reinterpret_cast<const uint4*>(smem);
+    z = z_;
+    dy = dy_;
+    p_begin = blockIdx.x * pg.per_cta;
+    p_end = min(pg.total, p_begin + pg.per_cta);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < NST; s++) mbar_init(bar0 + 8u * s, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  // piece p -> (b, first image row, x0, npx); for DYP = 2 the piece index runs over row PAIRS
+  __device__ __forceinline__ Piece piece(const Geo& g, const PieceGeo& pg, int p) const {
+    Geo gg = g;
+    gg.h = g.h / ROWS;
+    Piece q = piece_at(gg, pg, p);
+    q.y *= ROWS;
+    return q;
+  }
+  __device__ __forceinline__ void issue(const Geo& g, const PieceGeo& pg, int p) {   // thread 0 only
+    const int s = (p - p_begin) % NST;
+    const Piece q = piece(g, pg, p);
+    const uint32_t bytes = (uint32_t)q.npx * g.c * 2;
+    const uint32_t st = buf0 + s * STAGE_ITEMS * 16, bar = bar0 + 8u * s;
+    if (DYP == 0) {
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(st, z + pad_off(q.b, q.y, q.x0, g.h, g.w, g.c), bytes, bar);
+    } else if (DYP == 1) {
+      const size_t off = pad_off(q.b, q.y, q.x0, g.h, g.w, g.c);
+      mbar_expect_tx(bar, 2 * bytes);
+      bulk_g2s(st, z + off, bytes, bar);
+      bulk_g2s(st + Z_ITEMS * 16, dy + off, bytes, bar);
+    } else {
+      mbar_expect_tx(bar, 4 * bytes);
+      bulk_g2s(st, z + pad_off(q.b, q.y, q.x0, g.h, g.w, g.c), bytes, bar);
+      bulk_g2s(st + Z_ITEMS * 16, z + pad_off(q.b, q.y + 1, q.x0, g.h, g.w, g.c), bytes, bar);
+      bulk_g2s(st + 2 * Z_ITEMS * 16, dy + pad_off(q.b, q.y >> 1, q.x0 >> 1, g.h >> 1, g.w >> 1, 4 * g.c), 2 * bytes, bar);
+    }
+  }
+  __device__ __forceinline__ void prologue(const Geo& g, const PieceGeo& pg) {
+    if (threadIdx.x == 0)
+      for (int s = 0; s < NST && p_begin + s < p_end; s++) issue(g, pg, p_begin + s);
+  }
+  __device__ __forceinline__ const uint4* wait(int p) const {
+    const int it = p - p_begin, s = it % NST;
+    mbar_wait(bar0 + 8u * s, (uint32_t)(it / NST) & 1u);
+    return gen + (size_t)s * STAGE_ITEMS;
+  }
+  __device__ __forceinline__ void release(const Geo& g, const PieceGeo& pg, int p) {
+    __syncthreads();
+    if (threadIdx.x == 0 && p + NST < p_end) issue(g, pg, p + NST);
+  }
+  // dy of item i (pixel x0 + i / cgs, my channel group) of image row q.y + r, from the stage
+  __device__ __forceinline__ uint4 dy_item(const uint4* st, int i, int r, const RowSpan& rs, int cgs) const {
+    if (DYP == 1) return st[Z_ITEMS + i];
+    // s2d row: pixel pair j = (x - x0) / 2 holds 4 * cgs items, quadrant (row & 1) * 2 + (x & 1)   (x0 is even)
+    const int px = i >> rs.cgs_log2;
+    return st[2 * Z_ITEMS + (((px >> 1) * 4 + r * 2 + (px & 1)) << rs.cgs_log2) + rs.cg];
+  }
+};
+
 template <int DYP>
 __global__ void __launch_bounds__(BNT, 2) bn_act_bwd_reduce_pipe_kernel(
     const __nv_bfloat16* __restrict__ dy, int dcs, int up, const __nv_bfloat16* __restrict__ z, Geo g, PieceGeo pg,
@@ -200,17 +283,16 @@ __global__ void __launch_bounds__(BNT, 2) bn_act_bwd_reduce_pipe_kernel(
     const float* __restrict__ invstd, float slope, int has_act, float* __restrict__ sums /*[2*c + 1]*/,
     const float* __restrict__ slope_dev) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  constexpr int K = 1 + DYP, NST = DYP ? 2 : 4;
-  using Pipe = RowPipe<K, NST>;
+  using Pipe = BwdPipe<DYP>;
   Pipe pipe;
-  pipe.init(dsm, pg);
+  pipe.init(dsm, pg, z, dy);
   float* s_acc = reinterpret_cast<float*>(dsm + Pipe::smem_bytes());
   for (int i = threadIdx.x; i < 2 * g.c + 1; i += BNT) s_acc[i] = 0.f;
   __syncthreads();
-  const __nv_bfloat16* src[2] = {z, dy};
-  pipe.prologue(g, pg, src);
+  pipe.prologue(g, pg);
   if (slope_dev) slope = __ldg(slope_dev);
   const RowSpan rs = row_span(g);
+  const int cgs = g.c >> 3;
   float sc[8], sh[8], mu[8], is[8];
   load8(scale, rs.cg, sc);
   load8(shift, rs.cg, sh);
@@ -227,33 +309,36 @@ __global__ void __launch_bounds__(BNT, 2) bn_act_bwd_reduce_pipe_kernel(
     q1[e] = q2[e] = 0ull;
   }
   for (int p = pipe.p_begin; p < pipe.p_end; p++) {
-    const Piece q = piece_at(g, pg, p);
-    const uint4* zs = pipe.wait(p, 0);
-    const uint4* ds = DYP ? zs + PIPE_ITEMS : nullptr;
+    const Piece q = pipe.piece(g, pg, p);
+    const uint4* st = pipe.wait(p);
     const int items = q.npx << rs.cgs_log2;
-    for (int i = threadIdx.x; i < items; i += BNT) {
-      const uint4 zv = zs[i];
-      float d[8];
-      if (DYP) unpack8(ds[i], d);
-      else load_dy(dy, dcs, g, q.b, q.y, q.x0 + (i >> rs.cgs_log2), rs.cg, up, d);
-      const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const uint64_t f2 = bf2_to_f2(zw[e]);
-        float u0, u1;
-        f2unpack(f2fma(f2, sc2[e], sh2[e]), u0, u1);
-        float du0 = d[2 * e], du1 = d[2 * e + 1];
-        if (has_act) {
-          if (!(u0 > 0.f)) { asl = fmaf(du0, u0, asl); du0 *= slope; }
-          if (!(u1 > 0.f)) { asl = fmaf(du1, u1, asl); du1 *= slope; }
+    for (int r = 0; r < Pipe::ROWS; r++) {
+      const uint4* zs = st + r * Pipe::Z_ITEMS;
+      for (int i = threadIdx.x; i < items; i += BNT) {
+        const uint4 zv = zs[i];
+        float d[8];
+        if (DYP) unpack8(pipe.dy_item(st, i, r, rs, cgs), d);
+        else load_dy(dy, dcs, g, q.b, q.y, q.x0 + (i >> rs.cgs_log2), rs.cg, up, d);
+        const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const uint64_t f2 = bf2_to_f2(zw[e]);
+          float u0, u1;
+          f2unpack(f2fma(f2, sc2[e], sh2[e]), u0, u1);
+          float du0 = d[2 * e], du1 = d[2 * e + 1];
+          if (has_act) {
+            if (!(u0 > 0.f)) { asl = fmaf(du0, u0, asl); du0 *= slope; }
+            if (!(u1 > 0.f)) { asl = fmaf(du1, u1, asl); du1 *= slope; }
+          }
+          const uint64_t du2 = f2pack(du0, du1);
+          const uint64_t zh2 = f2mul(f2add(f2, nmu2[e]), is2[e]);
+          q1[e] = f2add(q1[e], du2);
+          q2[e] = f2fma(du2, zh2, q2[e]);
         }
-        const uint64_t du2 = f2pack(du0, du1);
-        const uint64_t zh2 = f2mul(f2add(f2, nmu2[e]), is2[e]);
-        q1[e] = f2add(q1[e], du2);
-        q2[e] = f2fma(du2, zh2, q2[e]);
       }
     }
-    pipe.release(g, pg, p, src);
+    pipe.release(g, pg, p);
   }
   float a1[8], a2[8];
 #pragma unroll
@@ -279,15 +364,14 @@ __global__ void __launch_bounds__(BNT, 2) bn_act_bwd_apply_pipe_kernel(
     const float* __restrict__ invstd, float slope, int has_act, int has_bn, const float* __restrict__ sums, float inv_n,
     __nv_bfloat16* __restrict__ gres, int gcs, int gres_acc, const float* __restrict__ slope_dev) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  constexpr int K = 1 + DYP, NST = DYP ? 2 : 4;
-  using Pipe = RowPipe<K, NST>;
+  using Pipe = BwdPipe<DYP>;
   Pipe pipe;
-  pipe.init(dsm, pg);
+  pipe.init(dsm, pg, z, dy);
   __syncthreads();
-  const __nv_bfloat16* src[2] = {z, dy};
-  pipe.prologue(g, pg, src);
+  pipe.prologue(g, pg);
   if (slope_dev) slope = __ldg(slope_dev);
   const RowSpan rs = row_span(g);
+  const int cgs = g.c >> 3;
   float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
   load8(scale, rs.cg, sc);
   load8(shift, rs.cg, sh);
@@ -306,76 +390,88 @@ __global__ void __launch_bounds__(BNT, 2) bn_act_bwd_apply_pipe_kernel(
     nm22[e] = f2pack(-m2[2 * e] * inv_n, -m2[2 * e + 1] * inv_n);
   }
   for (int p = pipe.p_begin; p < pipe.p_end; p++) {
-    const Piece q = piece_at(g, pg, p);
-    const int b = q.b, y = q.y;
-    __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, g.c) + rs.cg * 8;
-    __nv_bfloat16* gr = gres ? gres + pad_off(b, y, 0, g.h, g.w, gcs) + rs.cg * 8 : nullptr;
-    const uint4* zs = pipe.wait(p, 0);
-    const uint4* ds = DYP ? zs + PIPE_ITEMS : nullptr;
+    const Piece q = pipe.piece(g, pg, p);
+    const uint4* st = pipe.wait(p);
     const int items = q.npx << rs.cgs_log2;
-    for (int i = threadIdx.x; i < items; i += BNT) {
-      const int x = q.x0 + (i >> rs.cgs_log2);
-      const uint4 zv = zs[i];
-      float d[8];
-      if (DYP) unpack8(ds[i], d);
-      else load_dy(dy, dcs, g, b, y, x, rs.cg, up, d);
-      if (gr) {  // shortcut branch: d(residual) (+)= dy   (never combined with upsample)
-        float o[8];
-        if (gres_acc) {
-          unpack8(*reinterpret_cast<const uint4*>(gr + (size_t)x * gcs), o);
 #pragma unroll
-          for (int e = 0; e < 8; e++) o[e] += d[e];
-        } else {
+    for (int r = 0; r < Pipe::ROWS; r++) {
+      const int b = q.b, y = q.y + r;
+      __nv_bfloat16* zr = z + pad_off(b, y, 0, g.h, g.w, g.c) + rs.cg * 8;
+      __nv_bfloat16* gr = gres ? gres + pad_off(b, y, 0, g.h, g.w, gcs) + rs.cg * 8 : nullptr;
+      const uint4* zs = st + r * Pipe::Z_ITEMS;
+      for (int i = threadIdx.x; i < items; i += BNT) {
+        const int x = q.x0 + (i >> rs.cgs_log2);
+        const uint4 zv = zs[i];
+        float d[8];
+        if (DYP) unpack8(pipe.dy_item(st, i, r, rs, cgs), d);
+        else load_dy(dy, dcs, g, b, y, x, rs.cg, up, d);
+        if (gr) {  // shortcut branch: d(residual) (+)= dy   (never combined with upsample)
+          float o[8];
+          if (gres_acc) {
+            unpack8(*reinterpret_cast<const uint4*>(gr + (size_t)x * gcs), o);
 #pragma unroll
-          for (int e = 0; e < 8; e++) o[e] = d[e];
+            for (int e = 0; e < 8; e++) o[e] += d[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) o[e] = d[e];
+          }
+          *reinterpret_cast<uint4*>(gr + (size_t)x * gcs) = pack8(o);
         }
-        *reinterpret_cast<uint4*>(gr + (size_t)x * gcs) = pack8(o);
+        float out[8];
+        const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const uint64_t f2 = bf2_to_f2(zw[e]);
+          float u0, u1;
+          f2unpack(f2fma(f2, sc2[e], sh2[e]), u0, u1);
+          float du0 = d[2 * e], du1 = d[2 * e + 1];
+          if (has_act) {
+            if (!(u0 > 0.f)) du0 *= slope;
+            if (!(u1 > 0.f)) du1 *= slope;
+          }
+          if (has_bn) {
+            const uint64_t zh2 = f2mul(f2add(f2, nmu2[e]), is2[e]);
+            const uint64_t t2 = f2fma(zh2, nm22[e], f2add(f2pack(du0, du1), nm12[e]));
+            f2unpack(f2mul(sc2[e], t2), out[2 * e], out[2 * e + 1]);
+          } else {
+            out[2 * e] = du0;
+            out[2 * e + 1] = du1;
+          }
+        }
+        *reinterpret_cast<uint4*>(zr + (size_t)x * g.c) = pack8(out);
       }
-      float out[8];
-      const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const uint64_t f2 = bf2_to_f2(zw[e]);
-        float u0, u1;
-        f2unpack(f2fma(f2, sc2[e], sh2[e]), u0, u1);
-        float du0 = d[2 * e], du1 = d[2 * e + 1];
-        if (has_act) {
-          if (!(u0 > 0.f)) du0 *= slope;
-          if (!(u1 > 0.f)) du1 *= slope;
-        }
-        if (has_bn) {
-          const uint64_t zh2 = f2mul(f2add(f2, nmu2[e]), is2[e]);
-          const uint64_t t2 = f2fma(zh2, nm22[e], f2add(f2pack(du0, du1), nm12[e]));
-          f2unpack(f2mul(sc2[e], t2), out[2 * e], out[2 * e + 1]);
-        } else {
-          out[2 * e] = du0;
-          out[2 * e + 1] = du1;
-        }
-      }
-      *reinterpret_cast<uint4*>(zr + (size_t)x * g.c) = pack8(out);
     }
-    pipe.release(g, pg, p, src);
+    pipe.release(g, pg, p);
   }
 }
 
 // host side ------------------------------------------------------------------------------------------------------
-static inline int bn_pipe_mode() {     // measurement knob: RYOLO_BN_PIPE=0 selects the direct kernels
+// measurement knob RYOLO_BN_PIPE = bit mask of the passes that take the pipe: 1 stats, 2 forward, 4 backward.  Default 5:
+// the forward pass is write-limited and its direct version is already at 5.7-6.1 TB/s (profiles/r02_bn_sweep_pipe.txt:
+// pipe 5.3-5.7), statistics go 4.5 -> 6.3 TB/s and the backward pair 4.3 -> 6.4 TB/s through the pipe.
+constexpr int PIPE_STATS = 1, PIPE_FWD = 2, PIPE_BWD = 4;
+static inline int bn_pipe_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("RYOLO_BN_PIPE");
-    mode = e ? atoi(e) : 1;
+    mode = e ? atoi(e) : (PIPE_STATS | PIPE_BWD);
   }
   return mode;
 }
 // the pipe needs the rows of the tensor to be contiguous (channel stride == c) and 256 threads to tile the channel groups
-static inline bool pipe_ok(const Geo& g, int cstride) { return bn_pipe_mode() != 0 && cstride == g.c && (g.c >> 3) <= BNT; }
-static inline PieceGeo mk_pieces(const Geo& g, int* grid) {
+static inline bool pipe_ok(const Geo& g, int cstride, int pass) {
+  return (bn_pipe_mode() & pass) != 0 && cstride == g.c && (g.c >> 3) <= BNT;
+}
+// rows_per_piece = 2: row pairs with even piece boundaries and half-size z pieces (BwdPipe<2>)
+static inline PieceGeo mk_pieces(const Geo& g, int* grid, int rows_per_piece = 1) {
   PieceGeo pg;
   const int cgs = g.c >> 3;
-  const int max_px = PIPE_ITEMS / cgs;                 // >= 10 for c <= 1024
+  int max_px = PIPE_ITEMS / rows_per_piece / cgs;      // >= 10 for c <= 1024
+  if (rows_per_piece == 2) max_px &= ~1;
   pg.ppr = (g.w + max_px - 1) / max_px;
   pg.px = (g.w + pg.ppr - 1) / pg.ppr;
-  pg.total = g.batch * g.h * pg.ppr;
+  if (rows_per_piece == 2 && (pg.px & 1)) pg.px++;
+  pg.total = g.batch * (g.h / rows_per_piece) * pg.ppr;
   const int ctas = 2 * device_sm_count();
   pg.per_cta = (pg.total + ctas - 1) / ctas;
   *grid = (pg.total + pg.per_cta - 1) / pg.per_cta;

@@ -5,6 +5,7 @@ CONSUMER of the training hot path: tiny tensors, plain PyT
 Covered: the shipped configuration -- arc 'default' (separate obj / cls BCE), NoSampler, reject=True target assignment
 with the orphan-GT rescue.  Regression loss = SmoothL1(sigmoid xy) + 2 SmoothL1(theta) + giou * mean(1 - wh_iou): there
 is no rotated IoU in the reference loss."""
+import ctypes
 import math
 
 import torch
@@ -92,6 +93,8 @@ def compute_loss(p, targets, model, hyp):
     ~350 device-to-host reads per step); this evaluates the same sums over ALL (anchor, target) rows weighted by the 0/1
     assignment mask -- no host synchronisation.  tests/loss_indexed.py holds the literal indexed restatement and
     tests/test_loss.py proves the two equal (value, components, gradients) and pins both to the reference's outputs."""
+    if p[0].is_cuda and p[0].dtype == torch.float32:
+        return _compute_loss_fused(p, targets, model, hyp)
     if len(targets) == 0:
         return _compute_loss_no_targets(p, model)
     return _compute_loss_masked(p, targets, model, hyp)
@@ -110,6 +113,35 @@ def _compute_loss_no_targets(p, model):
     return lobj + zero, torch.cat((lobj, zero, zero, lobj)).detach()
 
 
+def _sparse_terms(ps, r, model, h, cls_pw):
+    """regression (+ class) loss of one head over ALL (anchor, target) rows weighted by the 0/1 assignment mask; ps =
+    pi[b, a, gj, gi] with the unselected rows already zeroed.  Returns (lreg_i, lcls_i), unweighted."""
+    av, tbox = r["av"], r["tbox"]
+    mf = r["mask"].to(ps.dtype)
+    cnt = mf.sum().clamp(min=1.0)              # an empty selection contributes 0 like the reference's `if nb:`
+    pxy = torch.sigmoid(ps[:, 0:2])
+    pwh = torch.exp(ps[:, 2:4]).clamp(max=1e3) * av[:, :-1]
+    pa = torch.atan(ps[:, 4]) + av[:, -1]
+    liou = ((1.0 - wh_iou(tbox[:, 2:4], pwh)) * mf).sum() / cnt
+    sm_xy = (nn.functional.smooth_l1_loss(pxy, tbox[:, 0:2], reduction="none") * mf[:, None]).sum() / (2.0 * cnt)
+    sm_a = (nn.functional.smooth_l1_loss(pa, tbox[:, 4], reduction="none") * mf).sum() / cnt
+    lreg = sm_xy + 2 * sm_a + liou * h["giou"]
+    lcls = None
+    if model.nc > 1:
+        t = torch.zeros_like(ps[:, 6:])
+        t[torch.arange(len(r["b"]), device=ps.device), r["tcls"]] = 1.0
+        e = nn.functional.binary_cross_entropy_with_logits(ps[:, 6:], t, pos_weight=cls_pw, reduction="none")
+        lcls = (e * mf[:, None]).sum() / (cnt * e.shape[1])
+    return lreg, lcls
+
+
+def _tobj_of(pi, r):
+    mf = r["mask"].to(pi.dtype)
+    tobj = torch.zeros(pi.shape[:4], dtype=pi.dtype, device=pi.device)
+    tobj.index_put_((r["b"], r["a"], r["gj"], r["gi"]), mf, accumulate=True)
+    return tobj.clamp_(max=1.0)
+
+
 def _compute_loss_masked(p, targets, model, hyp):
     dev = p[0].device
     h = model.hyp
@@ -123,30 +155,110 @@ def _compute_loss_masked(p, targets, model, hyp):
     BCEobj = nn.BCEWithLogitsLoss(pos_weight=torch.full((1,), float(h["obj_pw"]), device=dev))
     cls_pw = torch.full((1,), float(h["cls_pw"]), device=dev)
     for pi, r in zip(p, rows):
-        b, a, gj, gi, av, tbox = r["b"], r["a"], r["gj"], r["gi"], r["av"], r["tbox"]
-        mf = r["mask"].to(pi.dtype)
-        cnt = mf.sum().clamp(min=1.0)              # an empty selection contributes 0 like the reference's `if nb:`
-        tobj = torch.zeros_like(pi[..., 0])
-        tobj.index_put_((b, a, gj, gi), mf, accumulate=True)
-        tobj.clamp_(max=1.0)
-        ps = pi[b, a, gj, gi]
+        tobj = _tobj_of(pi, r)
+        ps = pi[r["b"], r["a"], r["gj"], r["gi"]]
         # rows the reference never touches must not poison the sums: exp(inf) * 0 would be NaN in forward AND backward
         ps = torch.where(r["mask"][:, None], ps, torch.zeros_like(ps))
-        pxy = torch.sigmoid(ps[:, 0:2])
-        pwh = torch.exp(ps[:, 2:4]).clamp(max=1e3) * av[:, :-1]
-        pa = torch.atan(ps[:, 4]) + av[:, -1]
-        liou = ((1.0 - wh_iou(tbox[:, 2:4], pwh)) * mf).sum() / cnt
-        sm_xy = (nn.functional.smooth_l1_loss(pxy, tbox[:, 0:2], reduction="none") * mf[:, None]).sum() / (2.0 * cnt)
-        sm_a = (nn.functional.smooth_l1_loss(pa, tbox[:, 4], reduction="none") * mf).sum() / cnt
-        lreg = lreg + sm_xy + 2 * sm_a + liou * h["giou"]
-        if model.nc > 1:
-            t = torch.zeros_like(ps[:, 6:])
-            t[torch.arange(len(b), device=dev), r["tcls"]] = 1.0
-            e = nn.functional.binary_cross_entropy_with_logits(ps[:, 6:], t, pos_weight=cls_pw, reduction="none")
-            lcls = lcls + (e * mf[:, None]).sum() / (cnt * e.shape[1])
+        lreg_i, lcls_i = _sparse_terms(ps, r, model, h, cls_pw)
+        lreg = lreg + lreg_i
+        if lcls_i is not None:
+            lcls = lcls + lcls_i
         lobj = lobj + BCEobj(pi[..., 5], tobj)
     lobj = lobj * h["obj"]
     lcls = lcls * h["cls"]
     lreg = lreg * h["reg"]
     loss = lobj + lcls + lreg
     return loss, torch.cat((lobj, lcls, lreg, loss)).detach()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA path: the dense objectness term and the whole head cotangent in two hand-written kernels (csrc/loss.cu)
+# ---------------------------------------------------------------------------------------------------------------
+class _FusedLoss(torch.autograd.Function):
+    """loss = obj * sum_i mean BCE(pi[..., 5], tobj_i) + reg * lreg + cls * lcls with the values of _compute_loss_masked.
+
+    forward : the matched rows are gathered (tiny [na*nt, no] tensors) and their terms -- and the gradient with respect to
+              the gathered rows -- evaluated with the same framework expressions as the masked form; the objectness term
+              over all 35 M cells is ONE kernel per head reading the head tensor through its strides (so the permuted
+              view of the NCHW buffer the head convolution wrote is consumed in place).
+    backward: ONE kernel per head writes the whole cotangent (objectness channel, zeros elsewhere) with the strides of
+              the input, the row gradients are scattered on top.  Nothing reads a device value on the host."""
+
+    @staticmethod
+    def forward(ctx, model, rows, h, *p):
+        from . import _lib
+        dev = p[0].device
+        cls_pw = torch.full((1,), float(h["cls_pw"]), device=dev)
+        lreg = torch.zeros(1, device=dev)
+        lcls = torch.zeros(1, device=dev)
+        row_grads = []
+        if rows is not None:
+            with torch.enable_grad():
+                gathered = []
+                sparse = torch.zeros(1, device=dev)
+                for pi, r in zip(p, rows):
+                    ps = pi.detach()[r["b"], r["a"], r["gj"], r["gi"]]
+                    ps = torch.where(r["mask"][:, None], ps, torch.zeros_like(ps)).requires_grad_()
+                    gathered.append(ps)
+                    lreg_i, lcls_i = _sparse_terms(ps, r, model, h, cls_pw)
+                    lreg = lreg + lreg_i.detach()
+                    sparse = sparse + lreg_i * h["reg"]
+                    if lcls_i is not None:
+                        lcls = lcls + lcls_i.detach()
+                        sparse = sparse + lcls_i * h["cls"]
+                row_grads = list(torch.autograd.grad(sparse, gathered))
+        sums = torch.zeros(len(p), dtype=torch.float64, device=dev)
+        tobjs, counts = [], []
+        st = _lib.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            for i, pi in enumerate(p):
+                B, na, ny, nx, no = pi.shape
+                tobj = _tobj_of(pi, rows[i]) if rows is not None else torch.zeros(pi.shape[:4], dtype=pi.dtype, device=dev)
+                strides = (ctypes.c_longlong * 5)(*pi.stride())
+                _lib.check(_lib.lib.ryolo_obj_bce_fwd(_lib.ptr(pi), strides, B, na, ny, nx, no, 5, _lib.ptr(tobj),
+                                                      float(h["obj_pw"]), ctypes.c_void_p(sums[i:].data_ptr()), st), "obj_bce_fwd")
+                tobjs.append(tobj)
+                counts.append(float(B * na * ny * nx))
+        lobj = sums[0] * (h["obj"] / counts[0])          # python scalars only: no host-to-device copy, no sync
+        for i in range(1, len(p)):
+            lobj = lobj + sums[i] * (h["obj"] / counts[i])
+        lobj = lobj.float().view(1)
+        lreg = lreg * h["reg"]
+        lcls = lcls * h["cls"]
+        loss = lobj + lcls + lreg
+        ctx.rows, ctx.tobjs, ctx.row_grads, ctx.counts = rows, tobjs, row_grads, counts
+        ctx.obj_w, ctx.obj_pw = float(h["obj"]), float(h["obj_pw"])
+        ctx.save_for_backward(*p)
+        items = torch.cat((lobj, lcls, lreg, loss)).detach()
+        ctx.mark_non_differentiable(items)
+        return loss, items
+
+    @staticmethod
+    def backward(ctx, gloss, _gitems):
+        from . import _lib
+        p = ctx.saved_tensors
+        dev = p[0].device
+        gloss = gloss.reshape(-1)[:1].float()
+        st = _lib.stream_ptr(dev)
+        grads = []
+        with torch.cuda.device(dev):
+            for i, pi in enumerate(p):
+                B, na, ny, nx, no = pi.shape
+                g = torch.empty_strided(pi.shape, pi.stride(), dtype=pi.dtype, device=dev)   # every element is written
+                scale = gloss * (ctx.obj_w / ctx.counts[i])
+                strides = (ctypes.c_longlong * 5)(*pi.stride())
+                _lib.check(_lib.lib.ryolo_obj_bce_bwd(_lib.ptr(pi), strides, B, na, ny, nx, no, 5, _lib.ptr(ctx.tobjs[i]),
+                                                      ctx.obj_pw, _lib.ptr(scale), _lib.ptr(g), st), "obj_bce_bwd")
+                if ctx.rows is not None:
+                    r = ctx.rows[i]
+                    g.index_put_((r["b"], r["a"], r["gj"], r["gi"]), ctx.row_grads[i] * gloss, accumulate=True)
+                grads.append(g)
+        return (None, None, None) + tuple(grads)
+
+
+def _compute_loss_fused(p, targets, model, hyp):
+    h = model.hyp
+    if "default" not in model.arc or "F" in model.arc:
+        raise NotImplementedError("only arc='default' is restated (the configuration the reference ships)")
+    rows = _targets_masked(model, targets, hyp) if len(targets) else None
+    return _FusedLoss.apply(model, rows, h, *p)

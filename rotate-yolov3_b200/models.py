@@ -438,7 +438,13 @@ class Darknet(nn.Module):
                 if self._tplan is None or self._tplan_key != key:
                     self._tplan = TrainPlan(self, b, h, w, x.device)
                     self._tplan_key = key
-                return list(DarknetTrainFn.apply(self._tplan, x, *list(self.parameters())))
+                raw = DarknetTrainFn.apply(self._tplan, x, *list(self.parameters()))     # fp32 NCHW head buffers
+                outs = []
+                for t, yi in zip(raw, self.yolo_layers):
+                    layer = self.module_list[yi]
+                    # model/models.py:190-192 without the .contiguous(): same values, the loss reads the view in place
+                    outs.append(t.view(b, layer.na, layer.nc + 6, t.shape[2], t.shape[3]).permute(0, 1, 3, 4, 2))
+                return outs
         with torch.cuda.device(x.device):
             # the plan holds PACKED (BN-folded, bf16) copies of the weights: rebuild it when any parameter or buffer was
             # modified in place since (optimizer step, manual edits); train()/eval()/load_state_dict drop it explicitly

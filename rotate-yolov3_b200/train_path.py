@@ -437,11 +437,9 @@ class TrainPlan:
         if bn_counters:
             with torch.no_grad():
                 torch._foreach_add_(bn_counters, 1)
-        outs = []
-        for blk, yi in zip(self.heads, m.yolo_layers):
-            layer = m.module_list[yi]
-            outs.append(blk.out.view(self.batch, layer.na, layer.nc + 6, blk.oh, blk.ow).permute(0, 1, 3, 4, 2).contiguous())
-        return outs
+        # the fp32 NCHW buffers the head convolutions wrote; DarknetTrainFn's caller hands out permuted VIEWS of them
+        # ([B, na, ny, nx, no] like model/models.py:190-192, without the .contiguous() copy of 0.5 GB per step)
+        return [blk.out for blk in self.heads]
 
     def forward(self, x):
         m = self.model
@@ -486,16 +484,17 @@ class TrainPlan:
 
     # ------------------------------------------------------------------------------------------------------
     def _head_grads(self, grads):
-        """autograd's head cotangents [B, na, ny, nx, no] -> bias gradients + padded-NHWC bf16 dz of the head convs"""
+        """autograd's head cotangents, fp32 NCHW [B, na*no, ny, nx] (the layout of the head buffers; contiguous without a
+        copy when the consumer differentiated the permuted view in place, as loss._FusedLoss does) -> bias gradients +
+        padded-NHWC bf16 dz of the head convs"""
         lib = _lib.lib
         st = _lib.stream_ptr(self.device)
         for blk, g in zip(self.heads, grads):
             g = g.contiguous().float()
-            na, no = g.shape[1], g.shape[4]
             if (blk.i, "Conv2d.bias") in self.param_slots:
-                torch.sum(g, (0, 2, 3), out=self.garena[blk.gb_off:blk.gb_off + blk.cout].view(na, no))
-            _lib.check(lib.ryolo_head_grad_to_padded(_lib.ptr(g), self.batch, na, no, blk.oh, blk.ow, _lib.ptr(blk.dz),
-                                                     blk.zcs, st), "head_grad_to_padded")
+                torch.sum(g, (0, 2, 3), out=self.garena[blk.gb_off:blk.gb_off + blk.cout])
+            _lib.check(lib.ryolo_head_grad_nchw_to_padded(_lib.ptr(g), self.batch, blk.cout, blk.oh, blk.ow, _lib.ptr(blk.dz),
+                                                          blk.zcs, st), "head_grad_nchw_to_padded")
 
     def _backward_block(self, blk):
         m = self.model
@@ -641,8 +640,7 @@ class DarknetTrainFn(torch.autograd.Function):
         gl = []
         for g, blk, yi in zip(grads, plan.heads, plan.model.yolo_layers):
             if g is None:
-                layer = plan.model.module_list[yi]
-                g = torch.zeros((plan.batch, layer.na, blk.oh, blk.ow, layer.nc + 6), dtype=torch.float32, device=plan.device)
+                g = torch.zeros((plan.batch, blk.cout, blk.oh, blk.ow), dtype=torch.float32, device=plan.device)
             gl.append(g)
         pg = plan.backward(gl)
         return (None, None) + tuple(pg)

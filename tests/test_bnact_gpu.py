@@ -13,8 +13,14 @@ def _bf(t):
     return t.to(torch.bfloat16).float()
 
 
+# up: False plain dy, True dy at 2x resolution (nearest-upsample adjoint), 2 dy in the space-to-depth layout of a following
+# 3x3/stride-2 block.  c = 32 / 48-wide strides take the direct kernels, the others the TMA row pipes (csrc/bnpipe.cuh);
+# the 200 x 200 cases span several pieces per row and wrap the shared-memory ring several times per CTA.
 @pytest.mark.parametrize("c,h,w,b,res,up", [(64, 6, 5, 3, False, False), (128, 9, 7, 2, True, False),
-                                            (256, 5, 4, 2, False, True), (32, 8, 8, 2, False, False)])
+                                            (256, 5, 4, 2, False, True), (32, 8, 8, 2, False, False),
+                                            (64, 200, 200, 4, True, False), (128, 8, 6, 2, False, 2),
+                                            (64, 200, 200, 3, False, 2), (32, 8, 8, 2, False, 2), (1024, 19, 19, 8, True, False),
+                                            (64, 120, 200, 2, False, True)])
 def test_bn_prelu_fwd_bwd_vs_autograd(c, h, w, b, res, up):
     import rotate_yolov3_b200 as pkg
     from rotate_yolov3_b200 import layout as L
@@ -26,6 +32,8 @@ def test_bn_prelu_fwd_bwd_vs_autograd(c, h, w, b, res, up):
     beta = (0.3 * torch.randn(c, generator=g)).to(dev)
     slope = 0.17
     r = _bf(torch.randn(b, c, h, w, generator=g)).to(dev) if res else None
+    s2d = up == 2
+    up = up is True
     oh, ow = (2 * h, 2 * w) if up else (h, w)
     dy = _bf(torch.randn(b, c, oh, ow, generator=g)).to(dev)
     # ---- torch reference ----
@@ -60,10 +68,13 @@ def test_bn_prelu_fwd_bwd_vs_autograd(c, h, w, b, res, up):
                                 cs, int(up), pt(sd), stream) == 0
     got_y = L.from_padded_nhwc(yb, c)
     assert float((got_y - y.detach()).abs().max()) <= 2.0 ** -7 * float(y.abs().max())
-    dyb = L.to_padded_nhwc(dy, cs)
+    dyb, dcs, mode = L.to_padded_nhwc(dy, cs), cs, int(up)
+    if s2d:     # [b, c, h, w] -> [b, 4c, h/2, w/2] with channel block (y & 1) * 2 + (x & 1), channel stride exactly 4c
+        q = torch.cat([dy[:, :, ry::2, rx::2] for ry in range(2) for rx in range(2)], 1)
+        dyb, dcs, mode = L.to_padded_nhwc(q, 4 * c), 4 * c, 2
     bs = torch.zeros(2 * c + 1, device=dev)
     grb = L.alloc_padded(b, h, w, cs, dev) if res else None
-    assert lib.ryolo_bn_act_bwd(pt(dyb), cs, int(up), pt(zb), cs, b, h, w, c, pt(scale), pt(shift), pt(mean.contiguous()),
+    assert lib.ryolo_bn_act_bwd(pt(dyb), dcs, mode, pt(zb), cs, b, h, w, c, pt(scale), pt(shift), pt(mean.contiguous()),
                                 pt(invstd.contiguous()), slope if res else -7.0, 1, 1, pt(bs), pt(grb) if res else None, cs, 0,
                                 None if res else pt(sd), stream) == 0
     torch.cuda.synchronize()
