@@ -350,9 +350,11 @@ int ryolo_nchw_to_padded(const float* src, int batch, int c, int h, int w, void*
 int ryolo_head_grad_to_padded(const float* g, int batch, int na, int no, int ny, int nx, void* dst,
                               int dst_cstride, void* stream);
 /* Same, for the cotangent in the layout the head convolution WROTE its output in: fp32 NCHW [B, C = na*no, ny, nx]
- * (what arrives when the consumer differentiates the permuted VIEW of that buffer, e.g. the fused loss below). */
+ * (what arrives when the consumer differentiates the permuted VIEW of that buffer, e.g. the fused loss below).
+ * bias_grad (nullable): [C] fp32, the per-channel sums of g are ADDED to it (the head convolution's bias gradient);
+ * C <= 2048. */
 int ryolo_head_grad_nchw_to_padded(const float* g, int batch, int c, int ny, int nx, void* dst,
-                                   int dst_cstride, void* stream);
+                                   int dst_cstride, float* bias_grad, void* stream);
 /* Objectness term of compute_loss (reference model/loss.py:340-348: BCEWithLogitsLoss(pos_weight)(pi[..., 5], tobj)
  * over every cell of a head map).  x: logical [batch, na, ny, nx, no] fp32 tensor addressed through `strides` (5 element
  * strides, so both the contiguous tensor and the permuted view of the NCHW head buffer are read in place); ch = the
@@ -363,6 +365,20 @@ int ryolo_obj_bce_fwd(const float* x, const long long* strides, int batch, int n
                       const float* tobj, float pos_weight, double* sum_out, void* stream);
 int ryolo_obj_bce_bwd(const float* x, const long long* strides, int batch, int na, int ny, int nx, int no, int ch,
                       const float* tobj, float pos_weight, const float* scale_dev, float* grad, void* stream);
+/* The matched (anchor, target) rows of compute_loss (reference model/loss.py:300-338 indexes `pi[b, a, gj, gi]`): int64
+ * device index vectors b / a / gj / gi and a 0/1 byte mask, `rows` entries each.  gather: out[r, k] = x[b, a, gj, gi, k]
+ * (0 for masked-out or out-of-range rows); set_tobj: tobj[b, a, gj, gi] = 1 (tobj contiguous [batch, na, ny, nx]);
+ * scatter_add: grad[b, a, gj, gi, k] += vals[r, k] * *scale_dev (atomic; duplicated cells accumulate like autograd's
+ * index backward).  x / grad are addressed through 5 element strides like ryolo_obj_bce_*. */
+int ryolo_loss_rows_gather(const float* x, const long long* strides, int batch, int na, int ny, int nx, int no,
+                           const long long* b, const long long* a, const long long* gj, const long long* gi,
+                           const unsigned char* mask, int rows, float* out, void* stream);
+int ryolo_loss_rows_scatter_add(float* grad, const long long* strides, int batch, int na, int ny, int nx, int no,
+                                const long long* b, const long long* a, const long long* gj, const long long* gi,
+                                const unsigned char* mask, int rows, const float* vals, const float* scale_dev,
+                                void* stream);
+int ryolo_loss_rows_set_tobj(float* tobj, int batch, int na, int ny, int nx, const long long* b, const long long* a,
+                             const long long* gj, const long long* gi, const unsigned char* mask, int rows, void* stream);
 /* im2col of the 3-channel fp32 image for the first 3x3 conv: bf16 padded NHWC with 64 channels
  * (27 real, column = c*9 + kh*3 + kw), so that the first layer runs on the same GEMM kernels. */
 int ryolo_im2col_first(const float* img, int batch, int h, int w, void* dst, void* stream);

@@ -68,33 +68,125 @@ __global__ void __launch_bounds__(256) obj_bce_bwd_kernel(const float* __restric
   }
 }
 
-// NCHW fp32 [B, C, ny, nx] -> padded-NHWC bf16 (channel stride dcs).  One block = 32 consecutive x of one image row, all
-// channels: 128-byte coalesced reads per channel, transposed through shared memory, 16-byte stores per pixel.
+// NCHW fp32 [B, C, ny, nx] -> padded-NHWC bf16 (channel stride dcs), plus the per-channel sums of g (the head convolution's
+// bias gradient) on the way.  One block = one image row: chunks of 32 consecutive x, 8 channels per warp and step (eight
+// 128-byte coalesced loads in flight per warp), transposed through shared memory with 16-byte stores whose row pitch is an
+// odd number of 16-byte units (conflict-free), 16-byte global stores of each pixel's contiguous channels.
 __device__ __forceinline__ size_t pad_off(int b, int y, int x, int h, int w, int cs) {
   return (((size_t)b * (h + 2) + y + 1) * (w + 2) + x + 1) * cs;
 }
+// sum over the 32 lanes of 8 per-lane values in 9 shuffles (halving exchange instead of 8 x 5 butterflies): on return
+// lanes 0, 4, .., 28 hold the total of value index lane / 4
+__device__ __forceinline__ float warp_sum8(const float* v, int lane) {
+  float a[4], b2[2], c1;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const float send = h16 ? v[e] : v[e + 4], keep = h16 ? v[e + 4] : v[e];
+    a[e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const float send = h8 ? a[e] : a[e + 2], keep = h8 ? a[e + 2] : a[e];
+    b2[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const float send = h4 ? b2[0] : b2[1], keep = h4 ? b2[1] : b2[0];
+    c1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+  c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
+  return c1;   // value index = 4 * (lane bit 4) + 2 * (lane bit 3) + (lane bit 2)
+}
+
 __global__ void __launch_bounds__(256) head_grad_nchw_kernel(const float* __restrict__ g, int c, int ny, int nx,
-                                                             __nv_bfloat16* __restrict__ dst, int dcs) {
+                                                             __nv_bfloat16* __restrict__ dst, int dcs,
+                                                             float* __restrict__ bias_grad, int rows_per_block) {
   extern __shared__ __align__(16) unsigned char hg_smem[];
+  const int c8 = (c + 7) & ~7;
+  const int cpad = c8 + ((c8 >> 3) & 1 ? 0 : 8);                      // pitch = odd multiple of 16 bytes
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(hg_smem);   // [32][cpad]
-  const int cpad = ((c + 7) & ~7) + 8;                                 // + 8: rows 16 B apart modulo the bank cycle
-  const int x0 = blockIdx.x * 32, y = blockIdx.y, b = blockIdx.z;
-  const int npx = min(32, nx - x0);
+  float* s_bias = reinterpret_cast<float*>(hg_smem + (size_t)32 * cpad * 2);   // [c8]: channel ch is owned by one warp
+  const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int ch = wid; ch < c; ch += 8)
-    if (lane < npx) tile[lane * cpad + ch] = __float2bfloat16_rn(__ldg(g + (((size_t)b * c + ch) * ny + y) * nx + x0 + lane));
+  for (int i = threadIdx.x; i < c8; i += 256) s_bias[i] = 0.f;
   __syncthreads();
-  const int chunks = c >> 3;
-  for (int idx = threadIdx.x; idx < npx * chunks; idx += 256) {
-    const int px = idx / chunks, k = idx - px * chunks;
-    *reinterpret_cast<uint4*>(dst + pad_off(b, y, x0 + px, ny, nx, dcs) + k * 8) =
-        *reinterpret_cast<const uint4*>(tile + px * cpad + k * 8);
+  const size_t plane = (size_t)ny * nx;
+  const int y_end = min(ny, (int)(blockIdx.x + 1) * rows_per_block);
+  for (int y = blockIdx.x * rows_per_block; y < y_end; y++) {
+    const float* grow = g + ((size_t)b * c * ny + y) * nx;
+    for (int x0 = 0; x0 < nx; x0 += 32) {
+      const int npx = min(32, nx - x0);
+#pragma unroll 1
+      for (int ch0 = wid * 8; ch0 < c8; ch0 += 64) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = (lane < npx && ch0 + e < c) ? __ldg(grow + (size_t)(ch0 + e) * plane + x0 + lane) : 0.f;
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        *reinterpret_cast<uint4*>(tile + lane * cpad + ch0) = *reinterpret_cast<uint4*>(h);
+        if (bias_grad) {
+          const float t = warp_sum8(v, lane);
+          if ((lane & 3) == 0) s_bias[ch0 + (lane >> 2)] += t;
+        }
+      }
+      __syncthreads();
+      const int chunks = c >> 3;
+      for (int idx = threadIdx.x; idx < npx * chunks; idx += 256) {
+        const int px = idx / chunks, k = idx - px * chunks;
+        *reinterpret_cast<uint4*>(dst + pad_off(b, y, x0 + px, ny, nx, dcs) + k * 8) =
+            *reinterpret_cast<const uint4*>(tile + px * cpad + k * 8);
+      }
+      const int tail = c & 7;
+      for (int idx = threadIdx.x; idx < npx * tail; idx += 256) {
+        const int px = idx / tail, e = (c & ~7) + idx % tail;
+        dst[pad_off(b, y, x0 + px, ny, nx, dcs) + e] = tile[px * cpad + e];
+      }
+      __syncthreads();
+    }
   }
-  const int tail = c & 7;
-  for (int idx = threadIdx.x; idx < npx * tail; idx += 256) {
-    const int px = idx / tail, e = (c & ~7) + idx % tail;
-    dst[pad_off(b, y, x0 + px, ny, nx, dcs) + e] = tile[px * cpad + e];
-  }
+  if (bias_grad)
+    for (int i = threadIdx.x; i < c; i += 256) atomicAdd(bias_grad + i, s_bias[i]);
+}
+
+// The matched (anchor, target) rows of compute_loss: gather of the head values at (b, a, gj, gi), the objectness targets,
+// and the scatter of the rows' gradients -- three tiny kernels instead of framework advanced indexing (each index op there
+// launches ~6 kernels: bounds reductions, asserts, the op itself).  Rows whose indices fall outside the map (a target on
+// the right / bottom border, where the reference raises an IndexError) and rows with mask == 0 read as 0 / write nothing.
+struct RowIdx {
+  const long long *b, *a, *gj, *gi;
+  const unsigned char* mask;
+  int rows;
+};
+__device__ __forceinline__ bool row_cell(const RowIdx& r, const HeadView& v, int i, size_t* off, size_t* cell) {
+  if (!r.mask[i]) return false;
+  const long long b = r.b[i], a = r.a[i], y = r.gj[i], x = r.gi[i];
+  if (b < 0 || b >= v.B || a < 0 || a >= v.na || y < 0 || y >= v.ny || x < 0 || x >= v.nx) return false;
+  *off = (size_t)(b * v.sb + a * v.sa + y * v.sy + x * v.sx);
+  *cell = (((size_t)b * v.na + a) * v.ny + y) * v.nx + x;
+  return true;
+}
+__global__ void rows_gather_kernel(const float* __restrict__ x, HeadView v, RowIdx r, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= r.rows * v.no) return;
+  const int i = t / v.no, k = t - i * v.no;
+  size_t off, cell;
+  out[t] = row_cell(r, v, i, &off, &cell) ? x[off + (size_t)k * v.sc] : 0.f;
+}
+__global__ void rows_scatter_add_kernel(float* __restrict__ g, HeadView v, RowIdx r, const float* __restrict__ vals,
+                                        const float* __restrict__ scale_dev) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= r.rows * v.no) return;
+  const int i = t / v.no, k = t - i * v.no;
+  size_t off, cell;
+  if (row_cell(r, v, i, &off, &cell)) atomicAdd(g + off + (size_t)k * v.sc, vals[t] * __ldg(scale_dev));
+}
+__global__ void rows_set_tobj_kernel(float* __restrict__ tobj, HeadView v, RowIdx r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r.rows) return;
+  size_t off, cell;
+  if (row_cell(r, v, i, &off, &cell)) tobj[cell] = 1.f;
 }
 
 static inline int loss_grid(size_t n) {
@@ -139,16 +231,70 @@ extern "C" int ryolo_obj_bce_bwd(const float* x, const long long* strides, int b
 }
 
 extern "C" int ryolo_head_grad_nchw_to_padded(const float* g, int batch, int c, int ny, int nx, void* dst, int dst_cstride,
-                                              void* stream_) {
+                                              float* bias_grad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RYOLO_ARG_CHECK(g && dst && batch > 0 && c > 0 && ny > 0 && nx > 0);
-  RYOLO_ARG_CHECK(dst_cstride >= c && dst_cstride % 8 == 0 && batch <= 65535 && ny <= 65535);
-  const int cpad = ((c + 7) & ~7) + 8;
-  const size_t smem = (size_t)32 * cpad * 2;
-  RYOLO_ARG_CHECK(smem <= 160 * 1024);
+  RYOLO_ARG_CHECK(dst_cstride >= c && dst_cstride % 8 == 0 && batch <= 65535 && c <= 2048);
+  const int c8 = (c + 7) & ~7;
+  const int cpad = c8 + ((c8 >> 3) & 1 ? 0 : 8);
+  const size_t smem = (size_t)32 * cpad * 2 + (size_t)c8 * sizeof(float);
   RYOLO_SMEM_OPT_IN(head_grad_nchw_kernel, 160 * 1024);
-  dim3 grid((unsigned)((nx + 31) / 32), (unsigned)ny, (unsigned)batch);
-  head_grad_nchw_kernel<<<grid, 256, smem, stream>>>(g, c, ny, nx, static_cast<__nv_bfloat16*>(dst), dst_cstride);
+  // rows per block: keep ~2k blocks in the grid (one set of c atomics per block for the bias gradient)
+  int rpb = (int)(((long long)ny * batch + 2047) / 2048);
+  if (rpb < 1) rpb = 1;
+  dim3 grid((unsigned)((ny + rpb - 1) / rpb), (unsigned)batch);
+  head_grad_nchw_kernel<<<grid, 256, smem, stream>>>(g, c, ny, nx, static_cast<__nv_bfloat16*>(dst), dst_cstride, bias_grad,
+                                                      rpb);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+static inline RowIdx mk_rows(const long long* b, const long long* a, const long long* gj, const long long* gi,
+                             const unsigned char* mask, int rows) {
+  RowIdx r;
+  r.b = b; r.a = a; r.gj = gj; r.gi = gi; r.mask = mask; r.rows = rows;
+  return r;
+}
+
+extern "C" int ryolo_loss_rows_gather(const float* x, const long long* strides, int batch, int na, int ny, int nx, int no,
+                                      const long long* b, const long long* a, const long long* gj, const long long* gi,
+                                      const unsigned char* mask, int rows, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  HeadView v;
+  RYOLO_ARG_CHECK(rows >= 0 && mk_view(strides, batch, na, ny, nx, no, &v));
+  if (rows == 0) return RYOLO_OK;
+  RYOLO_ARG_CHECK(x && b && a && gj && gi && mask && out);
+  rows_gather_kernel<<<(rows * no + 255) / 256, 256, 0, stream>>>(x, v, mk_rows(b, a, gj, gi, mask, rows), out);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_loss_rows_scatter_add(float* grad, const long long* strides, int batch, int na, int ny, int nx, int no,
+                                           const long long* b, const long long* a, const long long* gj, const long long* gi,
+                                           const unsigned char* mask, int rows, const float* vals, const float* scale_dev,
+                                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  HeadView v;
+  RYOLO_ARG_CHECK(rows >= 0 && mk_view(strides, batch, na, ny, nx, no, &v));
+  if (rows == 0) return RYOLO_OK;
+  RYOLO_ARG_CHECK(grad && b && a && gj && gi && mask && vals && scale_dev);
+  rows_scatter_add_kernel<<<(rows * no + 255) / 256, 256, 0, stream>>>(grad, v, mk_rows(b, a, gj, gi, mask, rows), vals,
+                                                                        scale_dev);
+  RYOLO_LAUNCH_CHECK();
+  return RYOLO_OK;
+}
+
+extern "C" int ryolo_loss_rows_set_tobj(float* tobj, int batch, int na, int ny, int nx, const long long* b, const long long* a,
+                                        const long long* gj, const long long* gi, const unsigned char* mask, int rows,
+                                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(rows >= 0 && batch > 0 && na > 0 && ny > 0 && nx > 0);
+  if (rows == 0) return RYOLO_OK;
+  RYOLO_ARG_CHECK(tobj && b && a && gj && gi && mask);
+  HeadView v;
+  v.sb = v.sa = v.sy = v.sx = v.sc = 0;
+  v.B = batch; v.na = na; v.ny = ny; v.nx = nx; v.no = 1;
+  rows_set_tobj_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(tobj, v, mk_rows(b, a, gj, gi, mask, rows));
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
 }

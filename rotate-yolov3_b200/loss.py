@@ -185,40 +185,54 @@ class _FusedLoss(torch.autograd.Function):
               the input, the row gradients are scattered on top.  Nothing reads a device value on the host."""
 
     @staticmethod
+    def _row_args(r):
+        from . import _lib
+        m8 = r["mask"].to(torch.uint8)
+        return (_lib.ptr(r["b"]), _lib.ptr(r["a"]), _lib.ptr(r["gj"]), _lib.ptr(r["gi"]), _lib.ptr(m8), int(r["b"].numel())), m8
+
+    @staticmethod
     def forward(ctx, model, rows, h, *p):
         from . import _lib
+        lib = _lib.lib
         dev = p[0].device
+        st = _lib.stream_ptr(dev)
         cls_pw = torch.full((1,), float(h["cls_pw"]), device=dev)
         lreg = torch.zeros(1, device=dev)
         lcls = torch.zeros(1, device=dev)
-        row_grads = []
-        if rows is not None:
-            with torch.enable_grad():
-                gathered = []
-                sparse = torch.zeros(1, device=dev)
-                for pi, r in zip(p, rows):
-                    ps = pi.detach()[r["b"], r["a"], r["gj"], r["gi"]]
-                    ps = torch.where(r["mask"][:, None], ps, torch.zeros_like(ps)).requires_grad_()
-                    gathered.append(ps)
-                    lreg_i, lcls_i = _sparse_terms(ps, r, model, h, cls_pw)
-                    lreg = lreg + lreg_i.detach()
-                    sparse = sparse + lreg_i * h["reg"]
-                    if lcls_i is not None:
-                        lcls = lcls + lcls_i.detach()
-                        sparse = sparse + lcls_i * h["cls"]
-                row_grads = list(torch.autograd.grad(sparse, gathered))
+        row_grads, tobjs, counts, keep = [], [], [], []
         sums = torch.zeros(len(p), dtype=torch.float64, device=dev)
-        tobjs, counts = [], []
-        st = _lib.stream_ptr(dev)
         with torch.cuda.device(dev):
+            gathered = []
             for i, pi in enumerate(p):
                 B, na, ny, nx, no = pi.shape
-                tobj = _tobj_of(pi, rows[i]) if rows is not None else torch.zeros(pi.shape[:4], dtype=pi.dtype, device=dev)
                 strides = (ctypes.c_longlong * 5)(*pi.stride())
-                _lib.check(_lib.lib.ryolo_obj_bce_fwd(_lib.ptr(pi), strides, B, na, ny, nx, no, 5, _lib.ptr(tobj),
-                                                      float(h["obj_pw"]), ctypes.c_void_p(sums[i:].data_ptr()), st), "obj_bce_fwd")
+                tobj = torch.zeros((B, na, ny, nx), dtype=pi.dtype, device=dev)
+                if rows is not None:
+                    r = rows[i]
+                    for key in ("b", "a", "gj", "gi"):
+                        r[key] = r[key].contiguous()
+                    ra, m8 = _FusedLoss._row_args(r)
+                    keep.append(m8)
+                    ps = torch.empty((ra[5], no), dtype=pi.dtype, device=dev)
+                    _lib.check(lib.ryolo_loss_rows_gather(_lib.ptr(pi), strides, B, na, ny, nx, no, *ra, _lib.ptr(ps), st),
+                               "loss_rows_gather")
+                    _lib.check(lib.ryolo_loss_rows_set_tobj(_lib.ptr(tobj), B, na, ny, nx, *ra, st), "loss_rows_set_tobj")
+                    gathered.append(ps.requires_grad_())
+                _lib.check(lib.ryolo_obj_bce_fwd(_lib.ptr(pi), strides, B, na, ny, nx, no, 5, _lib.ptr(tobj),
+                                                 float(h["obj_pw"]), ctypes.c_void_p(sums[i:].data_ptr()), st), "obj_bce_fwd")
                 tobjs.append(tobj)
                 counts.append(float(B * na * ny * nx))
+            if rows is not None:
+                with torch.enable_grad():
+                    sparse = torch.zeros(1, device=dev)
+                    for ps, r in zip(gathered, rows):
+                        lreg_i, lcls_i = _sparse_terms(ps, r, model, h, cls_pw)
+                        lreg = lreg + lreg_i.detach()
+                        sparse = sparse + lreg_i * h["reg"]
+                        if lcls_i is not None:
+                            lcls = lcls + lcls_i.detach()
+                            sparse = sparse + lcls_i * h["cls"]
+                    row_grads = [g_.contiguous() for g_ in torch.autograd.grad(sparse, gathered)]
         lobj = sums[0] * (h["obj"] / counts[0])          # python scalars only: no host-to-device copy, no sync
         for i in range(1, len(p)):
             lobj = lobj + sums[i] * (h["obj"] / counts[i])
@@ -226,7 +240,7 @@ class _FusedLoss(torch.autograd.Function):
         lreg = lreg * h["reg"]
         lcls = lcls * h["cls"]
         loss = lobj + lcls + lreg
-        ctx.rows, ctx.tobjs, ctx.row_grads, ctx.counts = rows, tobjs, row_grads, counts
+        ctx.rows, ctx.tobjs, ctx.row_grads, ctx.counts, ctx.keep = rows, tobjs, row_grads, counts, keep
         ctx.obj_w, ctx.obj_pw = float(h["obj"]), float(h["obj_pw"])
         ctx.save_for_backward(*p)
         items = torch.cat((lobj, lcls, lreg, loss)).detach()
@@ -236,22 +250,29 @@ class _FusedLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _gitems):
         from . import _lib
+        lib = _lib.lib
         p = ctx.saved_tensors
         dev = p[0].device
-        gloss = gloss.reshape(-1)[:1].float()
+        gloss = gloss.reshape(-1)[:1].float().contiguous()
         st = _lib.stream_ptr(dev)
         grads = []
         with torch.cuda.device(dev):
             for i, pi in enumerate(p):
                 B, na, ny, nx, no = pi.shape
+                # the cotangent gets the memory layout of the input: for the permuted view of an NCHW head buffer (what
+                # Darknet.forward returns) it reaches the network's backward as a contiguous NCHW tensor, no copy
                 g = torch.empty_strided(pi.shape, pi.stride(), dtype=pi.dtype, device=dev)   # every element is written
                 scale = gloss * (ctx.obj_w / ctx.counts[i])
                 strides = (ctypes.c_longlong * 5)(*pi.stride())
-                _lib.check(_lib.lib.ryolo_obj_bce_bwd(_lib.ptr(pi), strides, B, na, ny, nx, no, 5, _lib.ptr(ctx.tobjs[i]),
-                                                      ctx.obj_pw, _lib.ptr(scale), _lib.ptr(g), st), "obj_bce_bwd")
+                _lib.check(lib.ryolo_obj_bce_bwd(_lib.ptr(pi), strides, B, na, ny, nx, no, 5, _lib.ptr(ctx.tobjs[i]),
+                                                 ctx.obj_pw, _lib.ptr(scale), _lib.ptr(g), st), "obj_bce_bwd")
                 if ctx.rows is not None:
                     r = ctx.rows[i]
-                    g.index_put_((r["b"], r["a"], r["gj"], r["gi"]), ctx.row_grads[i] * gloss, accumulate=True)
+                    ra = (_lib.ptr(r["b"]), _lib.ptr(r["a"]), _lib.ptr(r["gj"]), _lib.ptr(r["gi"]), _lib.ptr(ctx.keep[i]),
+                          int(r["b"].numel()))
+                    _lib.check(lib.ryolo_loss_rows_scatter_add(_lib.ptr(g), strides, B, na, ny, nx, no, *ra,
+                                                               _lib.ptr(ctx.row_grads[i]), _lib.ptr(gloss), st),
+                               "loss_rows_scatter_add")
                 grads.append(g)
         return (None, None, None) + tuple(grads)
 

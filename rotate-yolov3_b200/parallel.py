@@ -133,3 +133,38 @@ class DistributedDataParallel(torch.nn.Module):
 
     def forward(self, *a, **k):
         return self.module(*a, **k)
+
+
+class DevicePrefetcher:
+    """Host -> device double buffering for the training loop (the reference copies each batch synchronously,
+    train.py:262-263 `imgs = imgs.to(device)`): the pinned host tensors of step i+1 are copied on a side stream while
+    step i computes; `get()` makes the compute stream wait for the copy it hands out.
+
+        pf = DevicePrefetcher(device)
+        pf.put(imgs_h, targets_h)                # start copying batch 0
+        for ...:
+            imgs, targets = pf.get()             # batch i on the device
+            pf.put(next_imgs_h, next_targets_h)  # batch i+1 copies while the step below runs
+            loss = ...; loss.backward(); opt.step()
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._pending = None
+
+    def put(self, *host_tensors):
+        with torch.cuda.stream(self.stream):
+            dev = [t.to(self.device, non_blocking=True) for t in host_tensors]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._pending = (dev, ev)
+
+    def get(self):
+        dev, ev = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in dev:
+            t.record_stream(cur)        # the caching allocator must not recycle it under the consumer
+        return dev

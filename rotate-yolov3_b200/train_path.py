@@ -491,10 +491,12 @@ class TrainPlan:
         st = _lib.stream_ptr(self.device)
         for blk, g in zip(self.heads, grads):
             g = g.contiguous().float()
-            if (blk.i, "Conv2d.bias") in self.param_slots:
-                torch.sum(g, (0, 2, 3), out=self.garena[blk.gb_off:blk.gb_off + blk.cout])
+            gb = self.garena[blk.gb_off:blk.gb_off + blk.cout] if (blk.i, "Conv2d.bias") in self.param_slots else None
+            if gb is not None:       # the bias gradient = per-channel sums of g, taken on the way by the same kernel
+                gb.zero_()
             _lib.check(lib.ryolo_head_grad_nchw_to_padded(_lib.ptr(g), self.batch, blk.cout, blk.oh, blk.ow, _lib.ptr(blk.dz),
-                                                          blk.zcs, st), "head_grad_nchw_to_padded")
+                                                          blk.zcs, _lib.ptr(gb) if gb is not None else None, st),
+                       "head_grad_nchw_to_padded")
 
     def _backward_block(self, blk):
         m = self.model

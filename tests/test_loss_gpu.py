@@ -101,7 +101,9 @@ def test_head_grad_nchw_to_padded_matches_layout():
         g = torch.randn(B, C, ny, nx, device=dev)
         cs = Lm.round_up(C, 32)
         dst = torch.full((B, ny + 2, nx + 2, cs), 7.0, dtype=torch.bfloat16, device=dev)
-        pkg._lib.check(lib.ryolo_head_grad_nchw_to_padded(P(g), B, C, ny, nx, P(dst), cs, pkg._lib.stream_ptr(dev)), "hg")
+        bias = torch.full((C,), 2.0, device=dev)
+        pkg._lib.check(lib.ryolo_head_grad_nchw_to_padded(P(g), B, C, ny, nx, P(dst), cs, P(bias), pkg._lib.stream_ptr(dev)), "hg")
         want = g.permute(0, 2, 3, 1).to(torch.bfloat16)
         assert torch.equal(dst[:, 1:-1, 1:-1, :C], want)
+        assert torch.allclose(bias - 2.0, g.sum((0, 2, 3)), rtol=1e-4, atol=1e-3)     # added to what was there
         assert bool((dst[:, 0] == 7.0).all()) and bool((dst[:, 1:-1, 1:-1, C:] == 7.0).all())

@@ -135,3 +135,20 @@ def test_sgd_step_reduces_a_toy_loss():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
+
+
+def test_device_prefetcher_hands_out_the_batches_in_order():
+    """parallel.DevicePrefetcher: batch i+1 is copied on a side stream while batch i is consumed; values and order kept"""
+    from rotate_yolov3_b200.parallel import DevicePrefetcher
+    dev = torch.device("cuda", 0)
+    pf = DevicePrefetcher(dev)
+    hosts = [(torch.full((4, 3, 64, 64), float(i)).pin_memory(), torch.arange(7.0).pin_memory() + i) for i in range(5)]
+    pf.put(*hosts[0])
+    acc = torch.zeros((), device=dev)
+    for i in range(5):
+        x, t = pf.get()
+        if i + 1 < 5:
+            pf.put(*hosts[i + 1])
+        assert x.device == dev and float(x.mean()) == float(i) and float(t[0]) == float(i)
+        acc = acc + x.sum() * 0 + t.sum()
+    assert float(acc) == sum(float(h[1].sum()) for h in hosts)
