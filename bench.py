@@ -336,9 +336,11 @@ def timed_steps(ctx, step, K, W, pre_step=None):
         step(i)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     sampler = ClockSampler(ctx.local_rank)
-    ctx.barrier()
     if ctx.rank == 0:
-        sampler.start()
+        sampler.start()          # BEFORE the barrier: starting it (nvml init, thread) takes tens of ms on rank 0 only, and a
+                                 # rank that enters the loop late makes the others wait inside their first timed all-reduce
+    torch.cuda.synchronize()
+    ctx.barrier()
     l0 = ctx.lib.ryolo_launch_count() + (ctx.replayed() if getattr(ctx, "replayed", None) else 0)
     for i in range(K):
         if pre_step:
@@ -562,8 +564,11 @@ def wl_train(ctx, K, W, full=True, precision="bf16"):
     model = parallel.DistributedDataParallel(net) if world > 1 else net     # train.py:175
     pg_w = [p for n, p in net.named_parameters() if "Conv2d.weight" in n]
     pg_o = [p for n, p in net.named_parameters() if "Conv2d.weight" not in n]
-    opt = torch.optim.SGD([{"params": pg_o}, {"params": pg_w, "weight_decay": 4.569e-4}], lr=1e-4, momentum=0.97,
-                          nesterov=True)                       # train.py:70-82 param groups, cfg/hyp_template.py
+    groups = [{"params": pg_o}, {"params": pg_w, "weight_decay": 4.569e-4}]      # train.py:70-82 param groups, cfg/hyp_template.py
+    try:        # the framework's single-kernel multi-tensor SGD (same update rule as train.py's optim.SGD)
+        opt = torch.optim.SGD(groups, lr=1e-4, momentum=0.97, nesterov=True, fused=True)
+    except (TypeError, RuntimeError):
+        opt = torch.optim.SGD(groups, lr=1e-4, momentum=0.97, nesterov=True)
     x_h = torch.rand(per_gpu, 3, 608, 608, generator=torch.Generator().manual_seed(ctx.rank)).pin_memory()
     tg_h = make_targets(per_gpu, 100 + ctx.rank).pin_memory()
     x, tg = x_h.to(dev), tg_h.to(dev)
@@ -818,8 +823,8 @@ def main():
     ctx.args, ctx.rank, ctx.world, ctx.local_rank = args, rank, world, local_rank
     ctx.dev = torch.device("cuda", local_rank)
     if world > 1:
-        # the gradient all-reduce runs NEXT to the backward GEMMs: cap the SMs NCCL may take (measured at 2 GPUs: 16 channels
-        # 40.4 ms/step, 8 channels 41.2; profiles/r02_n2_experiments.txt)
+        # the gradient all-reduce runs NEXT to the backward GEMMs: cap the SMs NCCL may take (at 2 GPUs 8 and 16 channels
+        # measure the same, profiles/r02_n2_experiments.txt)
         os.environ.setdefault("NCCL_MAX_NCHANNELS", "16")
         dist.init_process_group("nccl", device_id=ctx.dev)
     ctx.pk, ctx.pkg, ctx.lib = peaks(), pkg, pkg._lib.lib

@@ -10,42 +10,51 @@
 
 namespace ryolo {
 
-// grid = (chunks, jobs): a block belongs to ONE job (parameters uniform, no per-element search) and strides over its elements
+// grid = (chunks, jobs): a block belongs to ONE job (parameters uniform, no per-element search).  A thread owns one
+// (co, ci) PAIR and walks its taps: the k*k weights of a pair are contiguous in nn.Conv2d.weight (36-byte runs instead of nine
+// 4-byte reads a sector each), and each tap plane of the packed operand is written coalesced along ci.
 __global__ void __launch_bounds__(256) pack_multi_kernel(const ryolo_pack_job* __restrict__ jobs, int njobs,
                                                          const long long* __restrict__ prefix, long long total) {
   const ryolo_pack_job jb = jobs[blockIdx.y];
-  const long long n = prefix[blockIdx.y + 1] - prefix[blockIdx.y];
   const int plane = jb.cin_pad * jb.cout_pad;
+  const int taps = jb.ks * jb.ks;            // ks = taps per side of the PACKED operand (<= 3)
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(jb.packed);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(e / plane);
-    const int r = (int)(e - (long long)tap * plane);
-    const int co = r / jb.cin_pad, ci = r - co * jb.cin_pad;
-    float v = 0.f;
-    if (ci < jb.cin && co < jb.cout) v = pack_value(jb.weight, jb.cout, jb.cin, jb.ks, jb.mode, tap, co, ci);
-    out[e] = __float2bfloat16_rn(v);
+  for (int pair = blockIdx.x * blockDim.x + threadIdx.x; pair < plane; pair += gridDim.x * blockDim.x) {
+    const int co = pair / jb.cin_pad, ci = pair - co * jb.cin_pad;
+    const bool live = ci < jb.cin && co < jb.cout;
+    float v[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; tap++)
+      v[tap] = (live && tap < taps) ? pack_value(jb.weight, jb.cout, jb.cin, jb.ks, jb.mode, tap, co, ci) : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; tap++)
+      if (tap < taps) out[(size_t)tap * plane + pair] = __float2bfloat16_rn(v[tap]);
   }
 }
 
+// thread = one (co, c) pair of the parameter gradient: k*k reads, one per tap plane (coalesced along c), k*k contiguous writes
 __global__ void __launch_bounds__(256) unpack_multi_kernel(const ryolo_unpack_job* __restrict__ jobs, int njobs,
                                                            const long long* __restrict__ prefix, long long total) {
   const ryolo_unpack_job jb = jobs[blockIdx.y];
-  const long long n = prefix[blockIdx.y + 1] - prefix[blockIdx.y];
-  const int ks = jb.ks, kk = ks * ks;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(e % kk);
-    const int kw = t % ks, kh = t / ks;
-    const long long q = e / kk;
-    const int c = (int)(q % jb.cin);
-    const int co = (int)(q / jb.cin);
-    float v;
-    if (jb.mode == 0) {
-      v = jb.dw[((size_t)(kh * ks + kw) * jb.cout_pad + co) * jb.cin_pad + c];
-    } else {
-      const int qy = kh == 0 ? 0 : 1, py = kh == 1 ? 0 : 1, qx = kw == 0 ? 0 : 1, px = kw == 1 ? 0 : 1;
-      v = jb.dw[((size_t)(qy * 2 + qx) * jb.cout_pad + co) * jb.cin_pad + (py * 2 + px) * jb.cin + c];
+  const int ks = jb.ks, kk = ks * ks;        // ks = taps per side of the PARAMETER (1 or 3)
+  const int pairs = jb.cout * jb.cin;
+  for (int pair = blockIdx.x * blockDim.x + threadIdx.x; pair < pairs; pair += gridDim.x * blockDim.x) {
+    const int co = pair / jb.cin, c = pair - co * jb.cin;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      if (t >= kk) continue;
+      const int kw = t % ks, kh = t / ks;
+      if (jb.mode == 0) {
+        v[t] = jb.dw[((size_t)(kh * ks + kw) * jb.cout_pad + co) * jb.cin_pad + c];
+      } else {
+        const int qy = kh == 0 ? 0 : 1, py = kh == 1 ? 0 : 1, qx = kw == 0 ? 0 : 1, px = kw == 1 ? 0 : 1;
+        v[t] = jb.dw[((size_t)(qy * 2 + qx) * jb.cout_pad + co) * jb.cin_pad + (py * 2 + px) * jb.cin + c];
+      }
     }
-    jb.grad[e] = v;
+#pragma unroll
+    for (int t = 0; t < 9; t++)
+      if (t < kk) jb.grad[(size_t)pair * kk + t] = v[t];
   }
 }
 

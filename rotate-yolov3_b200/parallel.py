@@ -123,8 +123,8 @@ class DistributedDataParallel(torch.nn.Module):
         super().__init__()
         self.module = module
         # reserved_sms: SMs the backward GEMMs leave to the concurrent NCCL kernels.  Measured at 2 GPUs (profiles/
-        # r02_n2_experiments.txt): 0 is best (41.2 ms/step; 8 reserved: 44-56 ms, the tile counts of the 19^2 / 38^2 layers at
-        # 32 images no longer fit whole waves of 140 CTAs), so the default leaves every SM to the GEMMs
+        # r02_n2_experiments.txt, rank-0 step times): no measurable difference between 0 and 8, so the default leaves every SM
+        # to the GEMMs; the knob stays for larger rank counts
         import os
         reserved_sms = int(os.environ.get("RYOLO_DDP_RESERVED_SMS", reserved_sms))     # measurement knob
         module._ddp = {"bucket_bytes": int(bucket_mb) << 20, "group": process_group, "reserved_sms": int(reserved_sms)}

@@ -7,11 +7,12 @@ import subprocess
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(REPO, "build")
-MN = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "FADD2", "FMUL2", "FFMA2", "HMMA",
+MN = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCBAR", "SYNCS", "FADD2", "FMUL2", "FFMA2", "HMMA",
       "STG.E.EF", "RED.E", "ATOMS", "SHFL", "MUFU"]
 out = ["# SASS evidence, round 2 (cuobjdump -sass of the sm_100a objects linked into libryolo.so; nvcc 12.9, -O3 -lineinfo)",
        "# counts of instruction mnemonics per kernel: UTCHMMA = tcgen05.mma (kind::f16), UTMALDG / UTMASTG = TMA bulk tensor load /",
-       "# store, LDTM = tcgen05.ld (TMEM -> registers), UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, FADD2/FMUL2 = packed fp32x2.",
+       "# store, UBLKCP = cp.async.bulk (1-D TMA copy, the BN row pipes), LDTM = tcgen05.ld (TMEM -> registers), UTCBAR =",
+       "# tcgen05.commit, SYNCS = mbarrier ops, FADD2 / FMUL2 / FFMA2 = packed fp32x2.",
        "# Regenerate: python scratch/sass_summary.py", ""]
 for o in sorted(f for f in os.listdir(BUILD) if f.endswith(".o") and not f.startswith("rbox_oracle")):
     path = os.path.join(BUILD, o)
