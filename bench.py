@@ -342,6 +342,9 @@ def timed_steps(ctx, step, K, W, pre_step=None):
     torch.cuda.synchronize()
     ctx.barrier()
     l0 = ctx.lib.ryolo_launch_count() + (ctx.replayed() if getattr(ctx, "replayed", None) else 0)
+    prof = os.environ.get("RYOLO_BENCH_PROFILE_RANGE") == "1"      # `ncu --profile-from-start off`: the timed region only
+    if prof:
+        torch.cuda.profiler.start()
     for i in range(K):
         if pre_step:
             pre_step(i)          # e.g. L2 flush: outside the per-step events
@@ -349,6 +352,8 @@ def timed_steps(ctx, step, K, W, pre_step=None):
         step(i)
         ev[i][1].record()
     ctx.barrier()
+    if prof:
+        torch.cuda.profiler.stop()
     launches = ctx.lib.ryolo_launch_count() + (ctx.replayed() if getattr(ctx, "replayed", None) else 0) - l0
     clocks = sampler.stop() if ctx.rank == 0 else None
     per_step = [s.elapsed_time(e) for s, e in ev]

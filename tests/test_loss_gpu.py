@@ -107,3 +107,17 @@ def test_head_grad_nchw_to_padded_matches_layout():
         assert torch.equal(dst[:, 1:-1, 1:-1, :C], want)
         assert torch.allclose(bias - 2.0, g.sum((0, 2, 3)), rtol=1e-4, atol=1e-3)     # added to what was there
         assert bool((dst[:, 0] == 7.0).all()) and bool((dst[:, 1:-1, 1:-1, C:] == 7.0).all())
+
+
+def test_fused_loss_under_no_grad_and_with_detached_heads():
+    """test.py:96-98 evaluates compute_loss on the training-mode output under torch.no_grad(): same value, no graph"""
+    from rotate_yolov3_b200.loss import compute_loss
+    g, hyp = _golden()
+    dev = torch.device("cuda", 0)
+    ps = [torch.from_numpy(g["p%d" % k]).to(dev) for k in range(3)]
+    m = _fake_model([torch.from_numpy(g["p%d" % k]) for k in range(3)], hyp)
+    with torch.no_grad():
+        loss, items = compute_loss(ps, torch.from_numpy(g["targets"]).to(dev), m, hyp)
+    assert not loss.requires_grad
+    assert np.allclose(loss.cpu().numpy(), g["loss"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(items.cpu().numpy(), g["items"], rtol=1e-5, atol=1e-6)
