@@ -561,6 +561,8 @@ def wl_train(ctx, K, W, full=True, precision="bf16"):
     from rotate_yolov3_b200.loss import compute_loss
     pkg, dev, pk, world = ctx.pkg, ctx.dev, ctx.pk, ctx.world
     per_gpu = max(1, 64 // world)
+    if os.environ.get("RYOLO_BENCH_PER_GPU_BATCH"):        # experiment knob (scratch/): the per-rank load of an N-GPU run on one GPU
+        per_gpu = int(os.environ["RYOLO_BENCH_PER_GPU_BATCH"])
     net = pkg.Darknet(cfgs.yolov3_cfg(), dict(TRAIN_HYP), arc="default", precision=precision)
     helpers.init_darknet_weights(net, seed=1)
     net.nc, net.hyp = 1, dict(TRAIN_HYP)
@@ -636,7 +638,10 @@ def wl_train(ctx, K, W, full=True, precision="bf16"):
     plan = net._pplan if precision == "parity" else net._tplan
     if hasattr(plan, "time_comm"):
         plan.time_comm = True
+    torch.cuda.synchronize()
+    h0 = time.perf_counter()
     train_step(x, tg, tm)
+    ctx.host_ms_per_step = (time.perf_counter() - h0) * 1e3     # the HOST's time to enqueue one step on an idle device
     torch.cuda.synchronize()
     exposed = getattr(plan, "last_comm_wait_ms", lambda: None)()
     ctx.barrier()
@@ -654,6 +659,7 @@ def wl_train(ctx, K, W, full=True, precision="bf16"):
                                   "overlapped with backward" if world > 1 else "none (1 rank)",
                     "cuda_graph": bool(net.use_cuda_graph) if graph_note is None else graph_note,
                     "rank0_per_step_ms": getattr(ctx, "last_per_step", None),
+                    "rank0_host_enqueue_ms_per_step": round(getattr(ctx, "host_ms_per_step", 0.0), 3),
                     "reserved_sms": (net._ddp or {}).get("reserved_sms") if getattr(net, "_ddp", None) else 0,
                     "arithmetic": "bf16 operands/activations, fp32 accumulate and parameter gradients" if precision == "bf16"
                     else "fp32-grade: 3 bf16 planes per operand, 6 exact-product terms, fp32 round-to-nearest sums, fp64 "

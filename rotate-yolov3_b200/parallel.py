@@ -126,8 +126,9 @@ class DistributedDataParallel(torch.nn.Module):
         # r02_n2_experiments.txt, rank-0 step times): no measurable difference between 0 and 8, so the default leaves every SM
         # to the GEMMs; the knob stays for larger rank counts
         import os
-        reserved_sms = int(os.environ.get("RYOLO_DDP_RESERVED_SMS", reserved_sms))     # measurement knob
-        module._ddp = {"bucket_bytes": int(bucket_mb) << 20, "group": process_group, "reserved_sms": int(reserved_sms)}
+        reserved_sms = int(os.environ.get("RYOLO_DDP_RESERVED_SMS", reserved_sms))     # measurement knobs
+        bucket_mb = float(os.environ.get("RYOLO_DDP_BUCKET_MB", bucket_mb))
+        module._ddp = {"bucket_bytes": int(bucket_mb * (1 << 20)), "group": process_group, "reserved_sms": int(reserved_sms)}
         module._tplan = None          # the plan builds its buckets at construction
         module._pplan = None
 
