@@ -75,13 +75,14 @@ class YOLOLayer(nn.Module):
         if (self.nx, self.ny) != (nx, ny) or getattr(self, "_anchors_dev", None) is None or \
                 self._anchors_dev.device != p.device:
             self.create_grids(img_size, (nx, ny), p.device, p.dtype)
-        pp = torch.empty((bs, self.na, ny, nx, self.nc + 6), dtype=torch.float32, device=p.device)
+        # the raw head is handed out as the [B, na, ny, nx, no] VIEW of the NCHW buffer (model/models.py:190-192 without the
+        # .contiguous() copy: a third of this kernel's traffic), like the training path
         st = _lib.lib.ryolo_yolo_decode(_lib.ptr(p), bs, self.na, self.nc, ny, nx, _lib.ptr(self._anchors_dev),
                                         float(self.stride), float(self.hyp["context_factor"]),
                                         1 if "default" in self.arc else 0, _lib.ptr(io), rows_total, row_offset,
-                                        _lib.ptr(pp), _lib.stream_ptr(p.device))
+                                        None, _lib.stream_ptr(p.device))
         _lib.check(st, "ryolo_yolo_decode")
-        return pp
+        return p.view(bs, self.na, self.nc + 6, ny, nx).permute(0, 1, 3, 4, 2)
 
     def forward(self, p, img_size, var=None):
         if self.training:
