@@ -171,6 +171,84 @@ def _compute_loss_masked(p, targets, model, hyp):
     return loss, torch.cat((lobj, lcls, lreg, loss)).detach()
 
 
+def _targets_masked_stacked(model, targets, hyp):
+    """_targets_masked with the per-layer loop folded into a leading layer dimension (the CUDA path: a third of the tiny
+    element-wise launches).  Same element arithmetic; requires the same number of anchors in every YOLO layer.  Returns a
+    dict of [nl, R] (R = na * nt, row = a * nt + t) tensors: b, a, gj, gi (int64), mask (bool), tbox [nl, R, 5],
+    av [nl, R, 3], tcls [R]."""
+    nt = len(targets)
+    dev = targets.device
+    layers = [model.module_list[i] for i in model.yolo_layers]
+    nl = len(layers)
+    av_all = torch.stack([l.anchor_vec.to(dev) for l in layers], 0)              # [nl, na, 3]
+    ng = torch.stack([l.ng.to(dev) for l in layers], 0)                          # [nl, 2]
+    na = av_all.shape[1]
+    wh = []
+    for _ in range(nl):        # the reference compounds the context factor once per layer (loss.py:186-187): keep the order
+        targets[:, 4] += targets[:, 5] * (hyp["context_factor"] - 1)
+        targets[:, 5] *= hyp["context_factor"]
+        wh.append(targets[:, 4:6].clone())
+    wh = torch.stack(wh, 0) * ng[:, None, :]                                     # [nl, nt, 2] in grid units
+    ang = targets[:, 6]
+    w1, h1 = av_all[:, :, 0:1], av_all[:, :, 1:2]                                # [nl, na, 1]
+    w2, h2 = wh[:, None, :, 0], wh[:, None, :, 1]                                # [nl, 1, nt]
+    inter = torch.min(w1, w2) * torch.min(h1, h2)
+    all_ious = inter / ((w1 * h1 + 1e-16) + w2 * h2 - inter)                     # [nl, na, nt]
+    gxy = targets[None, :, 2:4] * ng[:, None, :]                                 # [nl, nt, 2]
+    gij = gxy.long()
+    gfrac = gxy - gxy.floor()
+    R = na * nt
+    rep = lambda x: x[:, None].expand(nl, na, *x.shape[1:]).reshape(nl, R, *x.shape[2:])     # [nl, nt, ..] -> [nl, R, ..]
+    a_idx = torch.arange(na, device=dev).view(-1, 1).expand(na, nt).reshape(-1)               # [R]
+    gwha = torch.cat((wh, ang.view(1, nt, 1).expand(nl, nt, 1)), 2)              # [nl, nt, 3]
+    tbox = torch.cat((rep(gfrac), rep(gwha)), 2)                                 # [nl, R, 5]
+    av = av_all[:, a_idx]                                                        # [nl, R, 3]
+    bc = targets[:, :2].long()
+    b_idx = bc[:, 0].repeat(na)
+    tcls = bc[:, 1].repeat(na)
+    # angle gate with the LAST layer's anchor angles (the reference's loop variable after the loop, loss.py:222-224)
+    angle_offset = (ang.view(1, nt) - av_all[-1, :, 2].view(na, 1)).abs()       # [na, nt]
+    angle_offset = torch.where(angle_offset > 0.5 * math.pi, math.pi - angle_offset, angle_offset)
+    j = (all_ious > model.hyp["iou_t"]) & (angle_offset < model.hyp["ang_t"])[None]          # [nl, na, nt]
+    gt_any = j.any(1).any(0)                                                     # [nt]
+    G = all_ious.reshape(nl * na, nt)
+    cand = G == G.max(0)[0]
+    layer_id = cand.float().argmax(0) // na
+    angr = angle_offset.repeat(nl, 1)
+    best = torch.where(cand, angr, torch.full_like(angr, float("inf"))).argmin(0)
+    anchor = best % na
+    onehot = torch.arange(na, device=dev).view(-1, 1) == anchor.view(1, -1)      # [na, nt]
+    rescue = (~gt_any) & (torch.arange(nl, device=dev).view(-1, 1) == layer_id.view(1, -1))   # [nl, nt]
+    mask = (j | (onehot[None] & rescue[:, None, :])).reshape(nl, R)
+    ex = lambda x: x[None].expand(nl, R).contiguous()
+    return dict(b=ex(b_idx), a=ex(a_idx), gj=rep(gij[..., 1:2]).reshape(nl, R).contiguous(),
+                gi=rep(gij[..., 0:1]).reshape(nl, R).contiguous(), mask=mask, tbox=tbox, av=av, tcls=tcls, nl=nl, R=R)
+
+
+def _sparse_terms_stacked(ps, r, model, h, cls_pw):
+    """_sparse_terms over all layers at once: ps [nl, R, no]; returns (lreg, lcls) summed over the layers, unweighted"""
+    av, tbox = r["av"], r["tbox"]
+    mf = r["mask"].to(ps.dtype)                                                   # [nl, R]
+    cnt = mf.sum(1).clamp(min=1.0)                                                # [nl]
+    pxy = torch.sigmoid(ps[..., 0:2])
+    pwh = torch.exp(ps[..., 2:4]).clamp(max=1e3) * av[..., :-1]
+    pa = torch.atan(ps[..., 4]) + av[..., -1]
+    w1, h1, w2, h2 = tbox[..., 2], tbox[..., 3], pwh[..., 0], pwh[..., 1]
+    inter = torch.min(w1, w2) * torch.min(h1, h2)
+    iou = inter / ((w1 * h1 + 1e-16) + w2 * h2 - inter)
+    liou = ((1.0 - iou) * mf).sum(1) / cnt
+    sm_xy = (nn.functional.smooth_l1_loss(pxy, tbox[..., 0:2], reduction="none") * mf[..., None]).sum((1, 2)) / (2.0 * cnt)
+    sm_a = (nn.functional.smooth_l1_loss(pa, tbox[..., 4], reduction="none") * mf).sum(1) / cnt
+    lreg = (sm_xy + 2 * sm_a + liou * h["giou"]).sum()
+    lcls = None
+    if model.nc > 1:
+        nc = ps.shape[-1] - 6
+        t = (torch.arange(nc, device=ps.device).view(1, 1, nc) == r["tcls"].view(1, -1, 1)).to(ps.dtype).expand(ps.shape[0], -1, -1)
+        e = nn.functional.binary_cross_entropy_with_logits(ps[..., 6:], t, pos_weight=cls_pw, reduction="none")
+        lcls = ((e * mf[..., None]).sum((1, 2)) / (cnt * nc)).sum()
+    return lreg, lcls
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # CUDA path: the dense objectness term and the whole head cotangent in two hand-written kernels (csrc/loss.cu)
 # ---------------------------------------------------------------------------------------------------------------
@@ -185,54 +263,53 @@ class _FusedLoss(torch.autograd.Function):
               the input, the row gradients are scattered on top.  Nothing reads a device value on the host."""
 
     @staticmethod
-    def _row_args(r):
+    def _row_ptrs(r, m8, i):
         from . import _lib
-        m8 = r["mask"].to(torch.uint8)
-        return (_lib.ptr(r["b"]), _lib.ptr(r["a"]), _lib.ptr(r["gj"]), _lib.ptr(r["gi"]), _lib.ptr(m8), int(r["b"].numel())), m8
+        step = r["R"] * 8
+        return (ctypes.c_void_p(r["b"].data_ptr() + i * step), ctypes.c_void_p(r["a"].data_ptr() + i * step),
+                ctypes.c_void_p(r["gj"].data_ptr() + i * step), ctypes.c_void_p(r["gi"].data_ptr() + i * step),
+                ctypes.c_void_p(m8.data_ptr() + i * r["R"]), int(r["R"]))
 
     @staticmethod
-    def forward(ctx, model, rows, h, *p):
+    def forward(ctx, model, r, h, *p):
         from . import _lib
         lib = _lib.lib
         dev = p[0].device
         st = _lib.stream_ptr(dev)
-        cls_pw = torch.full((1,), float(h["cls_pw"]), device=dev)
+        no = p[0].shape[-1]
         lreg = torch.zeros(1, device=dev)
         lcls = torch.zeros(1, device=dev)
-        row_grads, tobjs, counts, keep = [], [], [], []
+        tobjs, counts = [], []
+        row_grads = m8 = None
         sums = torch.zeros(len(p), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
-            gathered = []
+            if r is not None:
+                m8 = r["mask"].to(torch.uint8).contiguous()
+                ps_all = torch.empty((r["nl"], r["R"], no), dtype=p[0].dtype, device=dev)
             for i, pi in enumerate(p):
-                B, na, ny, nx, no = pi.shape
+                B, na, ny, nx, _ = pi.shape
                 strides = (ctypes.c_longlong * 5)(*pi.stride())
                 tobj = torch.zeros((B, na, ny, nx), dtype=pi.dtype, device=dev)
-                if rows is not None:
-                    r = rows[i]
-                    for key in ("b", "a", "gj", "gi"):
-                        r[key] = r[key].contiguous()
-                    ra, m8 = _FusedLoss._row_args(r)
-                    keep.append(m8)
-                    ps = torch.empty((ra[5], no), dtype=pi.dtype, device=dev)
-                    _lib.check(lib.ryolo_loss_rows_gather(_lib.ptr(pi), strides, B, na, ny, nx, no, *ra, _lib.ptr(ps), st),
-                               "loss_rows_gather")
+                if r is not None:
+                    ra = _FusedLoss._row_ptrs(r, m8, i)
+                    _lib.check(lib.ryolo_loss_rows_gather(_lib.ptr(pi), strides, B, na, ny, nx, no, *ra,
+                                                          ctypes.c_void_p(ps_all[i].data_ptr()), st), "loss_rows_gather")
                     _lib.check(lib.ryolo_loss_rows_set_tobj(_lib.ptr(tobj), B, na, ny, nx, *ra, st), "loss_rows_set_tobj")
-                    gathered.append(ps.requires_grad_())
                 _lib.check(lib.ryolo_obj_bce_fwd(_lib.ptr(pi), strides, B, na, ny, nx, no, 5, _lib.ptr(tobj),
                                                  float(h["obj_pw"]), ctypes.c_void_p(sums[i:].data_ptr()), st), "obj_bce_fwd")
                 tobjs.append(tobj)
                 counts.append(float(B * na * ny * nx))
-            if rows is not None:
+            if r is not None:
+                cls_pw = torch.full((1,), float(h["cls_pw"]), device=dev)
                 with torch.enable_grad():
-                    sparse = torch.zeros(1, device=dev)
-                    for ps, r in zip(gathered, rows):
-                        lreg_i, lcls_i = _sparse_terms(ps, r, model, h, cls_pw)
-                        lreg = lreg + lreg_i.detach()
-                        sparse = sparse + lreg_i * h["reg"]
-                        if lcls_i is not None:
-                            lcls = lcls + lcls_i.detach()
-                            sparse = sparse + lcls_i * h["cls"]
-                    row_grads = [g_.contiguous() for g_ in torch.autograd.grad(sparse, gathered)]
+                    ps_all.requires_grad_()
+                    lreg_s, lcls_s = _sparse_terms_stacked(ps_all, r, model, h, cls_pw)
+                    sparse = lreg_s * h["reg"]
+                    lreg = lreg + lreg_s.detach()
+                    if lcls_s is not None:
+                        sparse = sparse + lcls_s * h["cls"]
+                        lcls = lcls + lcls_s.detach()
+                    row_grads = torch.autograd.grad(sparse, ps_all)[0].contiguous()
         lobj = sums[0] * (h["obj"] / counts[0])          # python scalars only: no host-to-device copy, no sync
         for i in range(1, len(p)):
             lobj = lobj + sums[i] * (h["obj"] / counts[i])
@@ -240,7 +317,7 @@ class _FusedLoss(torch.autograd.Function):
         lreg = lreg * h["reg"]
         lcls = lcls * h["cls"]
         loss = lobj + lcls + lreg
-        ctx.rows, ctx.tobjs, ctx.row_grads, ctx.counts, ctx.keep = rows, tobjs, row_grads, counts, keep
+        ctx.rows, ctx.tobjs, ctx.row_grads, ctx.counts, ctx.keep = r, tobjs, row_grads, counts, m8
         ctx.obj_w, ctx.obj_pw = float(h["obj"]), float(h["obj_pw"])
         ctx.save_for_backward(*p)
         items = torch.cat((lobj, lcls, lreg, loss)).detach()
@@ -267,12 +344,10 @@ class _FusedLoss(torch.autograd.Function):
                 _lib.check(lib.ryolo_obj_bce_bwd(_lib.ptr(pi), strides, B, na, ny, nx, no, 5, _lib.ptr(ctx.tobjs[i]),
                                                  ctx.obj_pw, _lib.ptr(scale), _lib.ptr(g), st), "obj_bce_bwd")
                 if ctx.rows is not None:
-                    r = ctx.rows[i]
-                    ra = (_lib.ptr(r["b"]), _lib.ptr(r["a"]), _lib.ptr(r["gj"]), _lib.ptr(r["gi"]), _lib.ptr(ctx.keep[i]),
-                          int(r["b"].numel()))
+                    ra = _FusedLoss._row_ptrs(ctx.rows, ctx.keep, i)
                     _lib.check(lib.ryolo_loss_rows_scatter_add(_lib.ptr(g), strides, B, na, ny, nx, no, *ra,
-                                                               _lib.ptr(ctx.row_grads[i]), _lib.ptr(gloss), st),
-                               "loss_rows_scatter_add")
+                                                               ctypes.c_void_p(ctx.row_grads[i].data_ptr()), _lib.ptr(gloss),
+                                                               st), "loss_rows_scatter_add")
                 grads.append(g)
         return (None, None, None) + tuple(grads)
 
@@ -281,5 +356,8 @@ def _compute_loss_fused(p, targets, model, hyp):
     h = model.hyp
     if "default" not in model.arc or "F" in model.arc:
         raise NotImplementedError("only arc='default' is restated (the configuration the reference ships)")
-    rows = _targets_masked(model, targets, hyp) if len(targets) else None
+    nas = {int(pi.shape[1]) for pi in p}
+    if len(nas) != 1 or len({int(pi.shape[-1]) for pi in p}) != 1:      # ragged anchor counts: the per-layer framework form
+        return _compute_loss_masked(p, targets, model, hyp) if len(targets) else _compute_loss_no_targets(p, model)
+    rows = _targets_masked_stacked(model, targets, hyp) if len(targets) else None
     return _FusedLoss.apply(model, rows, h, *p)

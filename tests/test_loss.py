@@ -166,3 +166,44 @@ def test_loss_without_targets_and_with_poisoned_unselected_rows():
     loss2, _ = compute_loss(ps2, tg.clone(), m, hyp)
     loss2.backward()
     assert torch.isfinite(loss2).all() and all(torch.isfinite(p.grad).all() for p in ps2)
+
+
+def test_stacked_target_assignment_equals_the_per_layer_form():
+    """the CUDA path folds the per-layer loop of the target assignment / matched-row terms into a layer dimension
+    (loss._targets_masked_stacked, _sparse_terms_stacked): indices, masks and boxes must be IDENTICAL to the per-layer
+    form (which the tests above pin to the reference), also with a compounding context factor"""
+    from rotate_yolov3_b200 import loss as L
+    g = np.load(os.path.join(GOLDEN, "loss_golden.npz"))
+    hyp0 = {str(k): float(v) for k, v in zip(g["hyp_keys"], g["hyp_vals"])}
+    gen = torch.Generator().manual_seed(3)
+    for cf in (1.0, 1.3):
+        hyp = dict(hyp0)
+        hyp["context_factor"] = cf
+        for nc, nt in ((1, 40), (3, 17), (1, 1)):
+            shapes = [(2, 2, 4, 5, nc + 6), (2, 2, 8, 10, nc + 6), (2, 2, 16, 20, nc + 6)]
+            base = [torch.randn(s, generator=gen) for s in shapes]
+            t = torch.rand(nt, 7, generator=gen)
+            t[:, 0] = torch.randint(0, 2, (nt,), generator=gen).float()
+            t[:, 1] = torch.randint(0, nc, (nt,), generator=gen).float()
+            t[:, 2:4] = t[:, 2:4] * 0.98 + 0.01
+            t[:, 4:6] = t[:, 4:6] * 0.6 + 0.005
+            t[:, 6] = (t[:, 6] - 0.5) * 3.0
+            t[nt // 2] = t[0]
+            m = _fake_model(base, hyp)
+            m.nc = nc
+            rows = L._targets_masked(m, t.clone(), hyp)
+            st = L._targets_masked_stacked(m, t.clone(), hyp)
+            for l, r in enumerate(rows):
+                for k in ("b", "a", "gj", "gi", "mask"):
+                    assert torch.equal(r[k], st[k][l]), (k, l)
+                assert torch.equal(r["tbox"], st["tbox"][l]) and torch.equal(r["av"], st["av"][l])
+                assert torch.equal(r["tcls"], st["tcls"])
+            cls_pw = torch.full((1,), float(hyp["cls_pw"]))
+            ps = [torch.where(r["mask"][:, None], b_[r["b"], r["a"], r["gj"], r["gi"]], torch.zeros(1)) for b_, r in zip(base, rows)]
+            per = [L._sparse_terms(p_, r, m, hyp, cls_pw) for p_, r in zip(ps, rows)]
+            lreg2, lcls2 = L._sparse_terms_stacked(torch.stack(ps, 0), st, m, hyp, cls_pw)
+            lreg = sum(x[0] for x in per)
+            assert abs(float(lreg) - float(lreg2)) <= 1e-5 * abs(float(lreg))
+            if nc > 1:
+                lcls = sum(x[1] for x in per)
+                assert abs(float(lcls) - float(lcls2)) <= 1e-5 * abs(float(lcls))
