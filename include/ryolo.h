@@ -288,6 +288,12 @@ int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, int w, int c,
 /* sums -> per-channel mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, and (when the
  * pointers are non-null) the nn.BatchNorm2d running statistics update with momentum and the
  * unbiased variance (reference model/models.py:62: momentum 0.1, eps 1e-5). */
+/* ryolo_bn_stats + ryolo_bn_finalize in one call: when z's rows are contiguous (z_cstride == c) the last CTA of the
+ * statistics kernel to finish finalises (one launch per block instead of two); otherwise the two kernels run back to
+ * back.  sums: [2*c + 1] fp32 scratch (zeroed by the call; the extra word is the CTA ticket). */
+int ryolo_bn_stats_finalize(const void* z, int z_cstride, int batch, int h, int w, int c, float* sums, float eps,
+                            float momentum, const float* gamma, const float* beta, float* mean, float* invstd,
+                            float* scale, float* shift, float* running_mean, float* running_var, void* stream);
 int ryolo_bn_finalize(const float* sums, int c, float count, float eps, float momentum,
                       const float* gamma, const float* beta, float* mean, float* invstd,
                       float* scale, float* shift, float* running_mean, float* running_var,

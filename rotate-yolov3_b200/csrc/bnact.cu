@@ -587,8 +587,9 @@ extern "C" int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, in
     const PieceGeo pg = mk_pieces(g, &grid);
     constexpr size_t kMax = RowPipe<1, 4>::smem_bytes() + (2 * 2048 + 1) * sizeof(float);
     RYOLO_SMEM_OPT_IN(bn_stats_pipe_kernel, kMax);
+    BnFinalize none{};
     bn_stats_pipe_kernel<<<grid, BNT, RowPipe<1, 4>::smem_bytes() + 2 * c * sizeof(float), stream>>>(
-        static_cast<const __nv_bfloat16*>(z), g, pg, sums);
+        static_cast<const __nv_bfloat16*>(z), g, pg, sums, none);
     RYOLO_LAUNCH_CHECK();
     return RYOLO_OK;
   }
@@ -704,6 +705,39 @@ extern "C" int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, 
       gres_accumulate, rpb, slope_dev);
   RYOLO_LAUNCH_CHECK();
   return RYOLO_OK;
+}
+
+extern "C" int ryolo_bn_finalize(const float* sums, int c, float count, float eps, float momentum, const float* gamma,
+                                 const float* beta, float* mean, float* invstd, float* scale, float* shift,
+                                 float* running_mean, float* running_var, void* stream_);
+extern "C" int ryolo_bn_stats_finalize(const void* z, int z_cstride, int batch, int h, int w, int c, float* sums, float eps,
+                                       float momentum, const float* gamma, const float* beta, float* mean, float* invstd,
+                                       float* scale, float* shift, float* running_mean, float* running_var, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RYOLO_ARG_CHECK(z && sums && gamma && beta && mean && invstd && scale && shift);
+  RYOLO_ARG_CHECK((running_mean == nullptr) == (running_var == nullptr));
+  GEO_CHECK();
+  GEO_CHECK_P2();
+  const Geo g = mk_geo(batch, h, w, c);
+  const float count = (float)batch * h * w;
+  if (pipe_ok(g, z_cstride, PIPE_STATS)) {
+    RYOLO_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * (2 * c + 1), stream));      // sums + the ticket counter
+    int grid;
+    const PieceGeo pg = mk_pieces(g, &grid);
+    constexpr size_t kMax = RowPipe<1, 4>::smem_bytes() + (2 * 2048 + 1) * sizeof(float);
+    RYOLO_SMEM_OPT_IN(bn_stats_pipe_kernel, kMax);
+    BnFinalize fin;
+    fin.gamma = gamma; fin.beta = beta; fin.mean = mean; fin.invstd = invstd; fin.scale = scale; fin.shift = shift;
+    fin.running_mean = running_mean; fin.running_var = running_var; fin.count = count; fin.eps = eps; fin.momentum = momentum;
+    bn_stats_pipe_kernel<<<grid, BNT, RowPipe<1, 4>::smem_bytes() + 2 * c * sizeof(float), stream>>>(
+        static_cast<const __nv_bfloat16*>(z), g, pg, sums, fin);
+    RYOLO_LAUNCH_CHECK();
+    return RYOLO_OK;
+  }
+  int st = ryolo_bn_stats(z, z_cstride, batch, h, w, c, sums, stream_);
+  if (st != RYOLO_OK) return st;
+  return ryolo_bn_finalize(sums, c, count, eps, momentum, gamma, beta, mean, invstd, scale, shift, running_mean, running_var,
+                           stream_);
 }
 
 extern "C" int ryolo_bn_finalize(const float* sums, int c, float count, float eps, float momentum, const float* gamma,

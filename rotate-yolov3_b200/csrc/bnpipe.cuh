@@ -90,8 +90,29 @@ struct RowPipe {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// BN finalisation by the LAST CTA to finish (ticket counter behind the sums): saves one launch per block and step
+struct BnFinalize {
+  const float *gamma, *beta;        // gamma == nullptr: statistics only
+  float *mean, *invstd, *scale, *shift, *running_mean, *running_var;
+  float count, eps, momentum;
+};
+__device__ __forceinline__ void bn_finalize_channel(const BnFinalize& f, int c, int ch, float s1, float s2) {
+  const float mean = s1 / f.count;
+  const float var = fmaxf(s2 / f.count - mean * mean, 0.f);
+  const float invstd = rsqrtf(var + f.eps);
+  const float sc = f.gamma[ch] * invstd;
+  f.mean[ch] = mean;
+  f.invstd[ch] = invstd;
+  f.scale[ch] = sc;
+  f.shift[ch] = f.beta[ch] - mean * sc;
+  if (f.running_mean) {
+    f.running_mean[ch] = (1.f - f.momentum) * f.running_mean[ch] + f.momentum * mean;
+    f.running_var[ch] = (1.f - f.momentum) * f.running_var[ch] + f.momentum * var * (f.count / fmaxf(f.count - 1.f, 1.f));
+  }
+}
+
 __global__ void __launch_bounds__(BNT, 2) bn_stats_pipe_kernel(const __nv_bfloat16* __restrict__ z, Geo g, PieceGeo pg,
-                                                               float* __restrict__ sums /*[2*c]*/) {
+                                                               float* __restrict__ sums /*[2*c] (+ ticket)*/, BnFinalize fin) {
   extern __shared__ __align__(128) unsigned char dsm[];
   using Pipe = RowPipe<1, 4>;
   Pipe pipe;
@@ -134,6 +155,17 @@ __global__ void __launch_bounds__(BNT, 2) bn_stats_pipe_kernel(const __nv_bfloat
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * g.c; i += BNT) atomicAdd(&sums[i], s_acc[i]);
+  if (fin.gamma) {
+    __shared__ int s_last;
+    __threadfence();                       // my atomics before my ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(reinterpret_cast<unsigned int*>(sums + 2 * g.c), 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int ch = threadIdx.x; ch < g.c; ch += BNT) bn_finalize_channel(fin, g.c, ch, __ldcg(sums + ch), __ldcg(sums + g.c + ch));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -128,7 +128,7 @@ class TrainPlan:
                         blk.res, blk.gres = views[ridx], gviews[ridx]
                     else:
                         blk.res = blk.gres = None
-                    blk.sums = torch.zeros(2 * blk.cout, dtype=torch.float32, device=device)
+                    blk.sums = torch.zeros(2 * blk.cout + 1, dtype=torch.float32, device=device)      # + the CTA ticket of the fused finalize
                     blk.mean, blk.invstd, blk.scale, blk.shift = (torch.zeros(blk.cout, dtype=torch.float32, device=device)
                                                                   for _ in range(4))
                 blk.s2d = (i > 0 and blk.stride == 2 and blk.k == 3 and blk.src.h % 2 == 0 and blk.src.w % 2 == 0
@@ -411,12 +411,11 @@ class TrainPlan:
             cnt = n_per_pixel * blk.oh * blk.ow
             if blk.has_bn:
                 bn = seq.BatchNorm2d
-                _lib.check(lib.ryolo_bn_stats(_lib.ptr(blk.z), blk.zcs, self.batch, blk.oh, blk.ow, blk.cout,
-                                              _lib.ptr(blk.sums), st), "bn_stats")
-                _lib.check(lib.ryolo_bn_finalize(_lib.ptr(blk.sums), blk.cout, cnt, bn.eps, bn.momentum, _lib.ptr(bn.weight),
-                                                 _lib.ptr(bn.bias), _lib.ptr(blk.mean), _lib.ptr(blk.invstd),
-                                                 _lib.ptr(blk.scale), _lib.ptr(blk.shift), _lib.ptr(bn.running_mean),
-                                                 _lib.ptr(bn.running_var), st), "bn_finalize")
+                _lib.check(lib.ryolo_bn_stats_finalize(_lib.ptr(blk.z), blk.zcs, self.batch, blk.oh, blk.ow, blk.cout,
+                                                       _lib.ptr(blk.sums), bn.eps, bn.momentum, _lib.ptr(bn.weight),
+                                                       _lib.ptr(bn.bias), _lib.ptr(blk.mean), _lib.ptr(blk.invstd),
+                                                       _lib.ptr(blk.scale), _lib.ptr(blk.shift), _lib.ptr(bn.running_mean),
+                                                       _lib.ptr(bn.running_var), st), "bn_stats_finalize")
                 bn_counters.append(bn.num_batches_tracked)
             else:
                 raise NotImplementedError("conv block without BatchNorm that is not a YOLO head")

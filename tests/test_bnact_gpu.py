@@ -61,6 +61,16 @@ def test_bn_prelu_fwd_bwd_vs_autograd(c, h, w, b, res, up):
     invstd = torch.rsqrt(var + 1e-5)
     scale = (gamma * invstd).contiguous()
     shift = (beta - mean * scale).contiguous()
+    # statistics + finalisation in ONE call (last CTA of the statistics kernel finalises) == nn.BatchNorm2d's bookkeeping
+    f_sums = torch.full((2 * c + 1,), 3.0, device=dev)       # the call zeroes it (sums + ticket)
+    f_mean, f_inv, f_sc, f_sh = (torch.empty(c, device=dev) for _ in range(4))
+    rm, rv = torch.full((c,), 0.25, device=dev), torch.full((c,), 2.0, device=dev)
+    assert lib.ryolo_bn_stats_finalize(pt(zb), cs, b, h, w, c, pt(f_sums), 1e-5, 0.1, pt(gamma), pt(beta), pt(f_mean), pt(f_inv),
+                                       pt(f_sc), pt(f_sh), pt(rm), pt(rv), stream) == 0
+    assert torch.allclose(f_mean, mean, atol=1e-5) and torch.allclose(f_inv, invstd, rtol=1e-4)
+    assert torch.allclose(f_sc, scale, rtol=1e-4, atol=1e-6) and torch.allclose(f_sh, shift, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rm, 0.9 * 0.25 + 0.1 * mean, atol=1e-5)
+    assert torch.allclose(rv, 0.9 * 2.0 + 0.1 * var * (n / (n - 1)), rtol=1e-4, atol=1e-5)
     yb = L.alloc_padded(b, oh, ow, cs, dev)
     rb = L.to_padded_nhwc(r, cs) if res else None
     sd = torch.tensor([slope], device=dev)     # the slope as a device scalar (nn.PReLU.weight): overrides the host value
