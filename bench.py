@@ -12,11 +12,14 @@ bucketed NCCL all-reduce of the 62.4 M fp32 gradients overlaps backward.  The de
 (configs[2]) and detect e2e (configs[4]).
 A "step" is one pass of the hot path over one batch of synthetic input.  `value` is measured with inputs resident in
 HBM (CUDA events per step, max over ranks); `e2e` goes through the public Python API with pinned HOST buffers (H2D + D2H
-inside the timed region).  `roofline`: tensor pipe for the conv workloads (algorithmic FLOPs / measured sustained cuBLAS
+inside the timed region; for the training step ONE timed region around K/2 consecutive steps of the loop a user writes with
+`parallel.DevicePrefetcher`: batch i+1 copied under step i, batch 0 exposed, the loss on the host every step).  `roofline`: tensor pipe for the conv workloads (algorithmic FLOPs / measured sustained cuBLAS
 bf16 rate), HBM for IoU / NMS (algorithmic bytes / measured copy bandwidth).  `cpu_baseline` / `--impl reference` = the
 reference's own code on the host cores where it can be built (oracle/_ref: IoU, NMS), else a port executed by stock
 PyTorch CPU kernels (conv workloads; labelled).  The only place bench.py touches oracle/ is those CPU legs and the
-reference-CUDA-kernel baseline of the NMS line."""
+reference-CUDA-kernel baseline of the NMS line.
+Measurement knobs (scratch/ experiments, never set by default): RYOLO_BENCH_PER_GPU_BATCH (per-rank load of an N-GPU run on
+one GPU), RYOLO_BENCH_PROFILE_RANGE=1 (cudaProfilerStart/Stop around the timed region for `ncu --profile-from-start off`)."""
 import argparse
 import ctypes
 import json
