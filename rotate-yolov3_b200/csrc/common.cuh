@@ -86,6 +86,33 @@ inline int gemm_sm_count() {
     }                                                                                                         \
   } while (0)
 
+// Division of 0 <= n < 2^31 by a launch-invariant d >= 1 as a 64-bit multiply + shift: m = ceil(2^p / d), p = 31 + ceil(log2 d)
+// (exact: the error m*d - 2^p is < d <= 2^(p-31)).  An integer division by a runtime value costs ~25 instructions; the conv
+// epilogue did five per thread and tile -- 15 % of its instructions (ncu source page, profiles/r02_prof_conv_shapes_summary).
+struct FastDiv {
+  unsigned int m;
+  int p;
+  int d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  int l = 0;
+  while ((1ll << l) < d) l++;
+  f.p = 31 + l;
+  f.m = (unsigned int)(((1ull << f.p) + (unsigned long long)d - 1) / (unsigned long long)d);
+  f.d = d;
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+  return (int)(((unsigned long long)(unsigned int)n * f.m) >> f.p);
+}
+__device__ __forceinline__ void fast_divmod(int n, const FastDiv& f, int& q, int& r) {
+  q = fast_div(n, f);
+  r = n - q * f.d;
+}
+#endif
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // bump allocator over a caller-owned workspace

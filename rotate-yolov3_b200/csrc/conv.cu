@@ -136,6 +136,7 @@ struct ConvParams {
   const float* bias;               // [cout_pad]
   const __nv_bfloat16* residual;   // padded NHWC like the output, or null
   void* out;
+  FastDiv d_ntiles, d_wp, d_hp;    // divisions of the epilogue's per-tile index arithmetic
 };
 
 // NBUF = group buffers per epilogue team.  2 lets a residual group prefetch while the other buffer is processed; the
@@ -416,15 +417,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      int mt, nt;
+      fast_divmod(tile, p.d_ntiles, mt, nt);
       const int pix = mt * BM + row;  // flat padded input-grid pixel of this thread's row
       bool valid = pix < p.np;
       int b = 0, yp = 0, xp = 0;
       if (valid) {
-        xp = pix % p.wp;
-        const int t = pix / p.wp;
-        yp = t % p.hp;
-        b = t / p.hp;
+        int t;
+        fast_divmod(pix, p.d_wp, t, xp);
+        fast_divmod(t, p.d_hp, b, yp);
         valid = xp >= 1 && xp <= p.wp - 2 && yp >= 1 && yp <= p.hp - 2;
       }
       int oy = yp - 1, ox = xp - 1;
@@ -766,6 +767,9 @@ extern "C" int ryolo_conv_bn_act_fwd(const ryolo_conv_desc* d, const void* x, co
   p.cout = d->cout;
   p.cout_pad = g.cout_pad;
   p.n_tiles = g.cout_pad / g.bn;
+  p.d_ntiles = make_fastdiv(p.n_tiles);
+  p.d_wp = make_fastdiv(p.wp);
+  p.d_hp = make_fastdiv(p.hp);
   p.m_tiles = (p.np + BM - 1) / BM;
   p.stride = d->stride;
   p.oh = d->stride == 2 ? (d->in_h + 1) / 2 : d->in_h;   // k=3,pad=1 (or k=1,pad=0) with stride 2: ceil(h/2)
