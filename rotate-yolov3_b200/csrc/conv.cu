@@ -398,7 +398,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (;;) {
         const int tile = blockIdx.x + pit * gridDim.x;
         if (tile >= total_tiles) return;
-        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        int mt, nt;
+        fast_divmod(tile, p.d_ntiles, mt, nt);
         const int colbase = nt * BN + pg * 64;
         const bool live = colbase < p.store_cols;
         if (live && issuer) {
