@@ -584,7 +584,8 @@ extern "C" int ryolo_bn_stats(const void* z, int z_cstride, int batch, int h, in
   GEO_CHECK_P2();
   if (pipe_ok(g, z_cstride, PIPE_STATS)) {
     int grid;
-    const PieceGeo pg = mk_pieces(g, &grid);
+    PieceGeo pg = mk_pieces(g, &grid);
+    pg.rev = bn_reverse_mode() & 1;
     constexpr size_t kMax = RowPipe<1, 4>::smem_bytes() + (2 * 2048 + 1) * sizeof(float);
     RYOLO_SMEM_OPT_IN(bn_stats_pipe_kernel, kMax);
     BnFinalize none{};
@@ -674,12 +675,14 @@ extern "C" int ryolo_bn_act_bwd(const void* dy, int dy_cstride, int upsample2x, 
     __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(z_dz);
     __nv_bfloat16* grb = static_cast<__nv_bfloat16*>(gres);
     const size_t acc_bytes = (2 * c + 1) * sizeof(float);
+    PieceGeo pg_red = pg;                       // the reduction walks descending (it starts in the tail dgrad just wrote),
+    pg_red.rev = (bn_reverse_mode() >> 1) & 1;   // the apply pass ascending (it starts where the reduction ended)
 #define RYOLO_BWD_PIPE(D)                                                                                                  \
   do {                                                                                                                   \
     RYOLO_SMEM_OPT_IN(bn_act_bwd_reduce_pipe_kernel<D>, kMax);                                                           \
     RYOLO_SMEM_OPT_IN(bn_act_bwd_apply_pipe_kernel<D>, kMax);                                                            \
     bn_act_bwd_reduce_pipe_kernel<D><<<grid, BNT, BwdPipe<D>::smem_bytes() + acc_bytes, stream>>>(                       \
-        dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean, invstd, slope, has_act, sums, slope_dev);           \
+        dyb, dy_cstride, upsample2x, zb, g, pg_red, scale, shift, mean, invstd, slope, has_act, sums, slope_dev);           \
     RYOLO_LAUNCH_CHECK();                                                                                                \
     bn_act_bwd_apply_pipe_kernel<D><<<grid, BNT, BwdPipe<D>::smem_bytes(), stream>>>(                                    \
         dyb, dy_cstride, upsample2x, zb, g, pg, scale, shift, mean, invstd, slope, has_act, has_bn, sums, inv_cnt, grb,  \
@@ -723,9 +726,10 @@ extern "C" int ryolo_bn_stats_finalize(const void* z, int z_cstride, int batch, 
   if (pipe_ok(g, z_cstride, PIPE_STATS)) {
     RYOLO_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * (2 * c + 1), stream));      // sums + the ticket counter
     int grid;
-    const PieceGeo pg = mk_pieces(g, &grid);
+    PieceGeo pg = mk_pieces(g, &grid);
     constexpr size_t kMax = RowPipe<1, 4>::smem_bytes() + (2 * 2048 + 1) * sizeof(float);
     RYOLO_SMEM_OPT_IN(bn_stats_pipe_kernel, kMax);
+    pg.rev = bn_reverse_mode() & 1;
     BnFinalize fin;
     fin.gamma = gamma; fin.beta = beta; fin.mean = mean; fin.invstd = invstd; fin.scale = scale; fin.shift = shift;
     fin.running_mean = running_mean; fin.running_var = running_var; fin.count = count; fin.eps = eps; fin.momentum = momentum;

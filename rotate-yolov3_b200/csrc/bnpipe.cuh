@@ -1,11 +1,13 @@
 // TMA-fed versions of the four BN / PReLU passes (included by bnact.cu; same arithmetic, same results).
 //
+// Work split: the grid of <= 2 x SMs persistent CTAs strides over the row pieces together (piece = blockIdx + k * gridDim), so
+// the whole grid reads one moving front of the tensor.
 // Why: the direct versions keep ONE 16-byte load in flight per thread; at the 50-70 % occupancy their register budgets
 // allow that is ~23 KB in flight per SM, and Little's law (6.5 TB/s x ~0.8 us) asks for ~35 KB: they sit at 4.0-4.5 TB/s
 // (profiles/r02_prof_bn_summary.csv: DRAM 49 %, issue 55 %).  Unrolling for more loads per thread cost occupancy and was
 // slower (profiles/r02_bn_sweep.txt).  Here the bytes in flight are decoupled from the thread count: an interior row of
 // the padded-NHWC tensor is contiguous (w x c bf16 when the channel stride equals c, true for every z / dz buffer), so a
-// CTA walks a contiguous range of row PIECES (<= 20 KB), one elected thread issues `cp.async.bulk` (1-D TMA) copies of
+// CTA takes row PIECES (<= 20 KB) grid-stride, one elected thread issues `cp.async.bulk` (1-D TMA) copies of
 // the next pieces into a ring of shared-memory stages, completion on an mbarrier, and the 256 threads consume a stage
 // with LDS.128 -- 2 CTAs x 80 KB of stages per SM.  Stores go straight from registers (coalesced 16 B).
 #pragma once
@@ -19,8 +21,15 @@ struct PieceGeo {
   int ppr;       // pieces per interior row
   int px;        // pixels per piece (the last piece of a row may be shorter)
   int total;     // pieces in the tensor
-  int per_cta;   // contiguous pieces per CTA
+  int per_cta;   // pieces per CTA (grid = ceil(total / per_cta); the CTAs stride over the pieces together)
+  int rev;       // 1: the grid walks the tensor from the END (see "Traversal order" below)
 };
+
+// Traversal order.  A pass over a tensor larger than the 126 MB L2 that runs in the same direction as the pass before it
+// finds nothing of it in L2 (the lines it needs first were evicted first), while the opposite direction starts on the
+// ~100 MB the previous kernel touched LAST.  The chain per layer is  conv (writes z ascending) -> statistics -> bn_act_fwd
+// and  dgrad (writes dy ascending) -> reduce -> apply: statistics and reduce walk DESCENDING, bn_act_fwd and apply
+// ascending, so every pass begins inside its predecessor's tail.
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -47,14 +56,24 @@ template <int K, int NST>
 struct RowPipe {
   uint32_t buf0, bar0;
   const uint4* gen;       // generic-address view of the stage ring
-  int p_begin, p_end;
+  int p_begin, p_end, rev;
+
+  // ring slot p (0 <= p < p_end, consumed in increasing order) -> piece of the tensor: the grid strides over the pieces
+  // together, ascending or descending, so that the whole grid works on one moving front of the tensor
+  int total;
+  __device__ __forceinline__ int phys(int p) const {
+    const int k = blockIdx.x + p * gridDim.x;
+    return rev ? total - 1 - k : k;
+  }
 
   __device__ __forceinline__ void init(unsigned char* smem, const PieceGeo& pg) {
     buf0 = (uint32_t)__cvta_generic_to_shared(smem);
     bar0 = buf0 + NST * K * PIPE_STAGE_BYTES;
     gen = reinterpret_cast<const uint4*>(smem);
-    p_begin = blockIdx.x * pg.per_cta;
-    p_end = min(pg.total, p_begin + pg.per_cta);
+    rev = pg.rev;
+    total = pg.total;
+    p_begin = 0;
+    p_end = (int)blockIdx.x < pg.total ? (pg.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int s = 0; s < NST; s++) mbar_init(bar0 + 8u * s, 1);
@@ -66,7 +85,7 @@ struct RowPipe {
   // thread 0 only
   __device__ __forceinline__ void issue(const Geo& g, const PieceGeo& pg, int p, const __nv_bfloat16* const* src) {
     const int s = (p - p_begin) % NST;
-    const Piece q = piece_at(g, pg, p);
+    const Piece q = piece_at(g, pg, phys(p));
     const uint32_t bytes = (uint32_t)q.npx * g.c * 2;
     const size_t off = pad_off(q.b, q.y, q.x0, g.h, g.w, g.c);
     mbar_expect_tx(bar0 + 8u * s, bytes * K);
@@ -128,7 +147,7 @@ __global__ void __launch_bounds__(BNT, 2) bn_stats_pipe_kernel(const __nv_bfloat
   for (int e = 0; e < 4; e++) p1[e] = p2[e] = 0ull;
   for (int p = pipe.p_begin; p < pipe.p_end; p++) {
     const uint4* st = pipe.wait(p, 0);
-    const Piece q = piece_at(g, pg, p);
+    const Piece q = piece_at(g, pg, pipe.phys(p));
     const int items = q.npx << rs.cgs_log2;
     for (int i = threadIdx.x; i < items; i += BNT) {
       const uint4 v = st[i];
@@ -189,7 +208,7 @@ __global__ void __launch_bounds__(BNT, 2) bn_act_fwd_pipe_kernel(const __nv_bflo
   load8(scale, rs.cg, sc);
   load8(shift, rs.cg, sh);
   for (int p = pipe.p_begin; p < pipe.p_end; p++) {
-    const Piece q = piece_at(g, pg, p);
+    const Piece q = piece_at(g, pg, pipe.phys(p));
     const int b = q.b, yy = q.y;
     const __nv_bfloat16* rr = res ? res + pad_off(b, yy, 0, g.h, g.w, rcs) + rs.cg * 8 : nullptr;
     const uint4* st = pipe.wait(p, 0);
@@ -240,7 +259,7 @@ struct BwdPipe {
 
   uint32_t buf0, bar0;
   const uint4* gen;
-  int p_begin, p_end;
+  int p_begin, p_end, rev, total;
   const __nv_bfloat16 *z, *dy;
 
   __device__ __forceinline__ void init(unsigned char* smem, const PieceGeo& pg, const __nv_bfloat16* z_,
@@ -250,19 +269,22 @@ struct BwdPipe {
     gen = reinterpret_cast<const uint4*>(smem);
     z = z_;
     dy = dy_;
-    p_begin = blockIdx.x * pg.per_cta;
-    p_end = min(pg.total, p_begin + pg.per_cta);
+    rev = pg.rev;
+    total = pg.total;
+    p_begin = 0;
+    p_end = (int)blockIdx.x < pg.total ? (pg.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int s = 0; s < NST; s++) mbar_init(bar0 + 8u * s, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
-  // piece p -> (b, first image row, x0, npx); for DYP = 2 the piece index runs over row PAIRS
+  // ring slot p -> (b, first image row, x0, npx); for DYP = 2 the piece index runs over row PAIRS
   __device__ __forceinline__ Piece piece(const Geo& g, const PieceGeo& pg, int p) const {
     Geo gg = g;
     gg.h = g.h / ROWS;
-    Piece q = piece_at(gg, pg, p);
+    const int k = blockIdx.x + p * gridDim.x;                          // grid-stride, see "Traversal order"
+    Piece q = piece_at(gg, pg, rev ? total - 1 - k : k);
     q.y *= ROWS;
     return q;
   }
@@ -490,6 +512,15 @@ static inline int bn_pipe_mode() {
   }
   return mode;
 }
+// measurement knob RYOLO_BN_REVERSE: bit 0 statistics, bit 1 backward reduce walk their ranges descending (default 3)
+static inline int bn_reverse_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("RYOLO_BN_REVERSE");
+    mode = e ? atoi(e) : 3;
+  }
+  return mode;
+}
 // the pipe needs the rows of the tensor to be contiguous (channel stride == c) and 256 threads to tile the channel groups
 static inline bool pipe_ok(const Geo& g, int cstride, int pass) {
   return (bn_pipe_mode() & pass) != 0 && cstride == g.c && (g.c >> 3) <= BNT;
@@ -506,6 +537,7 @@ static inline PieceGeo mk_pieces(const Geo& g, int* grid, int rows_per_piece = 1
   pg.total = g.batch * (g.h / rows_per_piece) * pg.ppr;
   const int ctas = 2 * device_sm_count();
   pg.per_cta = (pg.total + ctas - 1) / ctas;
+  pg.rev = 0;
   *grid = (pg.total + pg.per_cta - 1) / pg.per_cta;
   return pg;
 }
