@@ -13,8 +13,9 @@
 //        dI/dc = Σ L_e n_e,   dI/dθ = Σ L_e n_e · perp(m_e − c),   dI/dw = ½ Σ_{e ∈ {u = ±w/2}} L_e,   dI/dh likewise.
 // e ∩ a is one parametric interval per edge (Liang–Barsky against a's four half-planes in a's frame) -- no polygon
 // clipping, no vertex arrays.  The gradient w.r.t. box a is the same computation with the roles swapped.
-// IoU = I / U, U = A_a + A_b − I:   dIoU = ((U + I) dI − I dA) / U².
+// IoU = I / U, U = A_a + A_b − I:   dIoU = ((U + I) dI − I dA) / U².  The value of I itself: clamp integral (see below).
 #include "common.cuh"
+#include "riou_area.cuh"
 
 namespace ryolo {
 
@@ -96,12 +97,12 @@ __global__ void __launch_bounds__(128) riou_grad_kernel(const float* __restrict_
   float dIa[5], dIb[5];
   edge_terms(A, B, dIa);      // a's edges inside b: dI/d(a)
   edge_terms(B, A, dIb);      // b's edges inside a: dI/d(b)
-  // The area itself from the SAME quantities (so value and gradient are consistent by construction) -- Euler's theorem:
-  // scaling both boxes about a common point p0 by lambda scales I by lambda^2; the generator of that scaling is
-  // (c − p0)·∇_c + w ∂_w + h ∂_h summed over both boxes, hence with p0 = c_a
-  //     2 I = w_a I_wa + h_a I_ha + w_b I_wb + h_b I_hb + (c_b − c_a)·∇_{c_b} I
-  const float dxw = B.cx - A.cx, dyw = B.cy - A.cy;
-  float I = 0.5f * (A.w * dIa[2] + A.h * dIa[3] + B.w * dIb[2] + B.h * dIb[3] + dxw * dIb[0] + dyw * dIb[1]);
+  // The area VALUE comes from the clamp integral of riou_area.cuh (the matrix kernel's routine): continuous and free of tie
+  // rules.  The edge terms above would give it too (Euler's theorem for the degree-2 homogeneity under common scaling:
+  // 2 I = w_a I_wa + h_a I_ha + w_b I_wb + h_b I_hb + (c_b − c_a)·∇_{c_b} I), but that sum counts a run where an edge of a
+  // lies ON an edge of b twice (once in each box's terms) -- exactly the axis-aligned, equal-height boxes detection data is
+  // full of; there the gradient is one-sided anyway, the value must still be right.
+  float I = clamp_integral_area2(A.cx, A.cy, A.c, A.s, 0.5f * A.w, 0.5f * A.h, B.cx, B.cy, B.c, B.s, 0.5f * B.w, 0.5f * B.h);
   const float Aa = A.w * A.h, Ab = B.w * B.h;
   const bool finite = isfinite(pa[0]) && isfinite(pa[1]) && isfinite(pa[2]) && isfinite(pa[3]) && isfinite(pa[4]) &&
                       isfinite(pb[0]) && isfinite(pb[1]) && isfinite(pb[2]) && isfinite(pb[3]) && isfinite(pb[4]);

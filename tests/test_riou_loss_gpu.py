@@ -93,3 +93,22 @@ def test_gradient_descent_on_riou_loss_aligns_boxes():
         loss.backward()
         opt.step()
     assert float(loss) < 0.6 * first, (first, float(loss))
+
+
+def test_axis_aligned_boxes_with_collinear_edges_have_the_right_value():
+    """boxes whose edges lie ON each other's edges (axis-aligned, equal height / same centre line: what detection labels are
+    full of): the value must be the true IoU.  An edge-clipping evaluation counts such a shared run twice; the kernel takes the
+    value from the clamp integral instead."""
+    from rotate_yolov3_b200.iou import rotated_iou
+    a = torch.tensor([[100.0, 100.0, 40.0, 20.0, 0.0], [100.0, 100.0, 40.0, 20.0, 0.0], [50.0, 60.0, 30.0, 30.0, 0.0],
+                      [100.0, 100.0, 40.0, 20.0, np.pi / 2], [10.0, 10.0, 8.0, 4.0, 0.0]])
+    b = torch.tensor([[120.0, 100.0, 40.0, 20.0, 0.0], [100.0, 100.0, 40.0, 20.0, 0.0], [65.0, 60.0, 30.0, 30.0, 0.0],
+                      [100.0, 120.0, 40.0, 20.0, np.pi / 2], [10.0, 12.0, 8.0, 4.0, 0.0]])
+    want = np.array([_oracle_iou(a[i].numpy(), b[i].numpy()) for i in range(len(a))])
+    assert abs(want[0] - 1.0 / 3.0) < 1e-9 and abs(want[1] - 1.0) < 1e-9
+    ad, bd = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    iou = rotated_iou(ad, bd)
+    got = iou.detach().cpu().numpy()
+    assert np.all(np.abs(got - want) <= 1e-4 * np.abs(want) + 1e-6), (got, want)
+    iou.sum().backward()
+    assert torch.isfinite(ad.grad).all() and torch.isfinite(bd.grad).all()
