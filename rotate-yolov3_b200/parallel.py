@@ -162,6 +162,8 @@ class DevicePrefetcher:
         self._pending = (dev, ev)
 
     def get(self):
+        if self._pending is None:
+            raise RuntimeError("DevicePrefetcher.get() without a pending batch: call put(...) first")
         dev, ev = self._pending
         self._pending = None
         cur = torch.cuda.current_stream(self.device)
